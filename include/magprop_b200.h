@@ -1,0 +1,170 @@
+/* magprop_b200.h -- C ABI of the B200-native magprop likelihood hot path.
+ *
+ * The reference (sgibson91/magprop) is pure Python and has NO FFI boundary; the
+ * path it runs per walker is
+ *     lnprob  -> lnprior -> lnlike -> model_lum/model_lc -> odeint(ODEs/odes)
+ *             -> luminosity stage -> interp1d -> chi-square
+ * (code/synthetic_datasets/mcmc_eqns.py:52-81, funcs.py:146-236 and
+ *  magnetar/mcmc_eqns.py:87-119, magnetar/funcs.py:105-220).
+ * This header is the boundary a maintainer binds with ctypes (INTEGRATION.md
+ * shows the stub); every entry point cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; all reals are
+ * IEEE binary64; row-major; every function returns an mp_status code except
+ * where noted; the library never falls back to a CPU implementation -- with no
+ * usable CUDA device every compute call returns MP_ERR_CUDA.
+ */
+#ifndef MAGPROP_B200_H
+#define MAGPROP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MP_ABI_VERSION 1
+#define MP_MAX_NDIM 9
+
+/* ---- return codes ------------------------------------------------------- */
+enum mp_status {
+  MP_OK = 0,
+  MP_ERR_BAD_ARG = 1,        /* null pointer, negative size, ndim not in 6..9            */
+  MP_ERR_DATA_RANGE = 2,     /* a data time lies outside the grid: interp1d raises        */
+                             /*   ValueError (funcs.py:233-234, magnetar/funcs.py:214)    */
+  MP_ERR_CUDA = 3,           /* CUDA runtime error / no device; mp_last_error() has text  */
+  MP_ERR_BAD_GRID = 4,       /* grid not strictly increasing or shorter than 2 nodes      */
+  MP_ERR_NO_DATA = 5         /* handle was created without data but a data call was made  */
+};
+
+/* ---- per-walker status word (bit field) ---------------------------------- */
+#define MP_WALKER_OK 0
+#define MP_WALKER_PRIOR_REJECT 1   /* lnprior == -inf (mcmc_eqns.py:43-49)                 */
+#define MP_WALKER_INTEGRATOR_FAIL 2 /* step budget / step underflow: the analogue of the   */
+                                   /*   reference's 'flag' (funcs.py:172-173) -> -inf      */
+#define MP_WALKER_NONFINITE_STATE 4 /* parameters outside the physical domain (NaN state): */
+                                   /*   luminosity is 0 as the reference's isfinite clamps */
+                                   /*   make it (funcs.py:216-227)                         */
+#define MP_WALKER_NONFINITE_LNLIKE 8 /* lnlike was NaN/inf -> -inf (mcmc_eqns.py:72-79)    */
+
+/* ---- model description ----------------------------------------------------
+ * One POD covers the reference's divergent copies of the model (script variant
+ * code/synthetic_datasets/funcs.py, packaged variant magnetar/funcs.py, figure
+ * scripts).  "rhs_*" are the knobs the ODE right-hand side sees, "lum_*" the
+ * ones the luminosity stage sees: the packaged model_lc does not forward its
+ * kwargs to odeint (magnetar/funcs.py:150-151), so they can differ.          */
+typedef struct mp_model_spec {
+  double inertia_factor;   /* I = f*M*R^2 : 0.35 (funcs.py:17) | 0.8 (magnetar/funcs.py:12)  */
+  double mdot_factor;      /* Rm ~ (f*Mdisc/tvisc)^(-2/7): 3 (funcs.py:105) | 1 (magnetar/funcs.py:64) */
+  double rhs_n, rhs_alpha, rhs_cs7, rhs_k;
+  double lum_n, lum_alpha, lum_cs7, lum_k;
+  double dipeff, propeff, f_beam;  /* defaults; theta[6..8] override per mp_model_spec.ndim rule */
+  double breakup_rhs;      /* rot_param > x => Nacc = 0 in the RHS (0.27: funcs.py:131)      */
+  double breakup_lum;      /* same test in the luminosity stage: 0.27 (funcs.py:206) | 0.0 (magnetar/funcs.py:193) */
+  int32_t lprop_binding_term; /* 1: Lprop = propeff*(-Nacc*w - GM/Rm*eta2*Mdot) (funcs.py:222-223); 0: propeff*(-Nacc*w) (magnetar/funcs.py:206) */
+  int32_t unlog_mask;      /* bit i set: theta[i] is log10 and is un-logged before the model (mcmc_eqns.py:17: bits 2..5) */
+  double rtol;             /* relative tolerance of the spin integrator (0 => default 1e-10) */
+  int32_t max_steps;       /* step budget per walker (0 => default 200000)                  */
+  int32_t reserved;
+} mp_model_spec;
+
+/* Top-hat prior: inclusive bounds, NaN rejects (mcmc_eqns.py:40-49,
+ * magnetar/mcmc_eqns.py:62-84 incl. the 7-parameter special case, which the
+ * caller resolves when filling lower/upper).  ndim entries are used.         */
+typedef struct mp_prior_spec {
+  int32_t ndim;
+  int32_t enabled;         /* 0: no prior test (model_lum / model_lc calls)                 */
+  double lower[MP_MAX_NDIM];
+  double upper[MP_MAX_NDIM];
+} mp_prior_spec;
+
+typedef struct mp_handle mp_handle;
+
+/* ---- lifetime ------------------------------------------------------------- */
+int mp_abi_version(void);
+int mp_device_count(void);                 /* number of CUDA devices (0 if none)            */
+const char* mp_last_error(void);           /* text of the last error on this thread          */
+
+/* Create a likelihood handle on `device`.
+ *   grid[G]          : the model time grid, np.logspace(0|-3, 6, 10001)
+ *                      (funcs.py:19, magnetar/funcs.py:132-141) -- passed in so its
+ *                      bits are the caller's NumPy bits
+ *   t,y,yerr[D]      : the burst data (x,y,yerr of generate_data.py:70 or
+ *                      t,Lum50,Lum50err of magnetar/mcmc_eqns.py:17-19); D may be 0
+ *                      (t=y=yerr=NULL) for a curves-only handle
+ * The handle owns device copies of everything it is given.                      */
+int mp_create(const mp_model_spec* spec, const mp_prior_spec* prior,
+              const double* grid, int32_t G,
+              const double* t, const double* y, const double* yerr, int32_t D,
+              int32_t device, mp_handle** out);
+void mp_destroy(mp_handle* h);
+int mp_set_prior(mp_handle* h, const mp_prior_spec* prior);
+
+/* ---- the hot path ----------------------------------------------------------
+ * lnprob for W walkers in one launch: replaces  [lnprob(theta_i, x, y, yerr, fbad)
+ * for i in walkers]  (mcmc_eqns.py:52-81; emcee's compute_log_prob with
+ * vectorize=True).  theta is [W][ndim] row-major.  lnp[W] receives lnprior+lnlike
+ * or -inf (never NaN).  status[W] (may be NULL) receives the MP_WALKER_* bits,
+ * n_rhs[W] (may be NULL) the number of right-hand-side evaluations spent.
+ * Host-pointer form: copies in, launches, copies out, synchronises.            */
+int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int32_t ndim,
+                    double* lnp, int32_t* status, int32_t* n_rhs);
+
+/* Device-pointer form: all pointers are device addresses on the handle's device
+ * (e.g. torch.Tensor.data_ptr()); enqueues on `stream` (a cudaStream_t, NULL =
+ * default stream) and returns without synchronising.                           */
+int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32_t W, int32_t ndim,
+                           double* d_lnp, int32_t* d_status, int32_t* d_n_rhs,
+                           void* stream);
+
+/* Model luminosity at the data times, /1e50: replaces model_lum(pars, xdata=x)
+ * (funcs.py:233-236) / model_lc(pars, xdata=x, ...) (magnetar/funcs.py:213-217).
+ * pars is [W][ndim] PHYSICAL parameters (no un-logging, no prior); out is [W][D];
+ * status[W] may be NULL (MP_WALKER_INTEGRATOR_FAIL <=> the 'flag' return).      */
+int mp_model_at_data(mp_handle* h, const double* pars, int32_t W, int32_t ndim,
+                     double* out, int32_t* status);
+
+/* Full light curves: replaces model_lum(pars) / model_lc(pars) with xdata=None
+ * (funcs.py:230-231, magnetar/funcs.py:219-220).  Every node_stride-th grid node
+ * is produced (0, s, 2s, ...; the last grid node is appended if not hit):
+ * Gs = mp_curve_nodes(h, node_stride).  out is [W][3][Gs] = Ltot, Lprop, Ldip
+ * (/1e50).  state (may be NULL) is [W][2][Gs] = Mdisc, omega at those nodes
+ * (the odeint solution of tests/test_funcs.py:28-48).                           */
+int32_t mp_curve_nodes(const mp_handle* h, int32_t node_stride);
+int mp_model_curves(mp_handle* h, const double* pars, int32_t W, int32_t ndim,
+                    int32_t node_stride, double* out, double* state, int32_t* status);
+int mp_model_curves_device(mp_handle* h, const double* d_pars, int32_t W, int32_t ndim,
+                           int32_t node_stride, double* d_out, double* d_state,
+                           int32_t* d_status, void* stream);
+
+/* Right-hand side of the coupled ODEs for a batch of states, computed on the
+ * device: replaces ODEs(y,t,B,MdiscI,RdiscI,epsilon,delta,n,alpha,cs7,k)
+ * (funcs.py:75-142) / odes(...) (magnetar/funcs.py:33-101).
+ * y [W][2], t [W], pars [W][5] = B,MdiscI,RdiscI,epsilon,delta; knobs [4] =
+ * n,alpha,cs7,k; dydt [W][2].  Host pointers.                                   */
+int mp_rhs_batch(const mp_model_spec* spec, const double* y, const double* t,
+                 const double* pars, const double* knobs, int32_t W, double* dydt,
+                 int32_t device);
+
+/* One emcee-style stretch-move half-step on the device (synth_mcmc.py:180-185
+ * configures emcee's default StretchMove(a=2)): proposes for the Ns walkers of
+ * `d_active` (indices into the ensemble) from the complementary set, evaluates
+ * lnprob, accepts/rejects in place -- one fused launch.  Counter-based RNG
+ * (Philox4x32-10) keyed by seed with counter (step, walker), so any rank can
+ * reproduce any walker's draws.  d_accepted[nwalkers] (may be NULL) counts
+ * acceptances, d_n_rhs[nwalkers] (may be NULL) receives the RHS evaluations.
+ * All pointers are device pointers.                                             */
+int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_lnp, int32_t nwalkers,
+                         int32_t ndim, const int32_t* d_active, int32_t n_active,
+                         const int32_t* d_complement, int32_t n_complement,
+                         double a, uint64_t seed, uint64_t step, int32_t* d_accepted,
+                         int32_t* d_n_rhs, void* stream);
+
+/* FP64 FMA peak micro-benchmark (roofline denominator; MEASURED_PEAKS.json has
+ * no FP64 entry): returns achieved TFLOP/s of dependent-chain-free DFMA.        */
+int mp_fp64_peak_tflops(int32_t device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAGPROP_B200_H */

@@ -1,0 +1,559 @@
+// magprop_core.cuh -- per-walker arithmetic of the magprop likelihood hot path.
+//
+// One walker = one thread.  Everything here is straight-line FP64 code on
+// registers plus a small per-thread node buffer; the kernels in
+// magprop_kernels.cu wrap it.  (tests/hostsim compiles this same header with
+// g++ to debug the algorithm in the GPU-less build container; that build is
+// test infrastructure and is never loaded by the package.)
+//
+// Reference behaviour reproduced (file:line are relative to the reference):
+//   init_conds            code/synthetic_datasets/funcs.py:51-71, magnetar/funcs.py:17-29
+//   ODEs / odes           funcs.py:75-142, magnetar/funcs.py:33-101
+//   luminosity stage      funcs.py:175-229, magnetar/funcs.py:157-210
+//   interp1d + /1e50      funcs.py:233-236, magnetar/funcs.py:213-217
+//   lnlike/lnprior/lnprob mcmc_eqns.py:5-81, magnetar/mcmc_eqns.py:6-119
+//
+// How the ODE system is solved:
+//   * eta1 + eta2 = 1, so dMdisc/dt = Mdot_fb(t) - Mdisc/tvisc is linear and
+//     independent of omega.  It is evaluated in closed form,
+//         Mdisc(t) = K S(u) + C exp(-(u-u0)),  u = (t+tfb)/tvisc,
+//     with S tabulated to 7e-16 (disc_table.inc).  This removes the
+//     -Mdisc/tvisc stiffness that makes explicit RK need 1e4..1e5 steps.
+//   * the remaining scalar spin equation is integrated by Dormand-Prince 5(4)
+//     with the Hairer-Norsett-Wanner PI step controller and 4th-order dense
+//     output, evaluated at the grid nodes the data need.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MP_HD __host__ __device__ __forceinline__
+#define MP_TABLE_QUALIFIER __device__ const
+#else
+#define MP_HD inline
+#define MP_TABLE_QUALIFIER static const
+#endif
+
+#include "disc_table.inc"
+
+namespace mp {
+
+// ---- physical constants: funcs.py:12-18, magnetar/funcs.py:7-13 -------------
+constexpr double kG = 6.674e-8;
+constexpr double kC = 3.0e10;
+constexpr double kR = 1.0e6;
+constexpr double kMsol = 1.99e33;
+constexpr double kM = 1.4 * kMsol;
+constexpr double kGM = kG * kM;
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+constexpr int kWalkerOk = 0;
+constexpr int kWalkerPriorReject = 1;
+constexpr int kWalkerIntegratorFail = 2;
+constexpr int kWalkerNonfiniteState = 4;
+constexpr int kWalkerNonfiniteLnlike = 8;
+
+// Device-side copy of mp_model_spec plus derived walker-independent constants.
+struct Spec {
+  double inertia;        // I
+  double inv_inertia;
+  double mdot_factor;
+  double rhs_n, rhs_tv_per_R, rhs_k;       // tvisc = RdiscI * rhs_tv_per_R
+  double lum_n, lum_tv_per_R, lum_k;
+  double dipeff, propeff, f_beam;
+  double omega2_breakup_rhs;   // omega^2 above which rot_param > breakup_rhs
+  double omega2_breakup_lum;
+  double sqrt_GMR;             // sqrt(GM*R): lever arm when Rm < R
+  int lprop_binding_term;
+  int unlog_mask;
+  double rtol;
+  int max_steps;
+};
+
+// Grid nodes and data laid out for the kernel (device pointers).
+struct DataView {
+  int n_nodes;             // nodes the evaluation needs, ascending in time
+  int n_data;
+  const double* node_t;    // [n_nodes]
+  const double* dat_y;     // [n_data] sorted by time
+  const double* dat_yerr;  // [n_data]
+  const double* dat_dx;    // [n_data] x - t_lo            (0 when x is a grid node)
+  const double* dat_Dx;    // [n_data] t_hi - t_lo         (1 when x is a grid node)
+  const int* dat_lo;       // [n_data] index into node_t of the lower bracketing node
+  double t_start;          // grid[0]: where the initial conditions hold
+};
+
+// ---- the disc-mass kernel function S(u) ----------------------------------
+MP_HD double ldg(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
+MP_HD int64_t dbits(double x) {
+#if defined(__CUDA_ARCH__)
+  return __double_as_longlong(x);
+#else
+  union { double d; int64_t i; } v; v.d = x; return v.i;
+#endif
+}
+MP_HD double bitsd(int64_t i) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double(i);
+#else
+  union { double d; int64_t i; } v; v.i = i; return v.d;
+#endif
+}
+
+MP_HD double disc_S(double u) {
+  const int64_t b = dbits(u);
+  const int e = (int)((b >> 52) & 0x7ff) - 1023;
+  if (e >= MP_DISC_EMIN && e <= MP_DISC_EMAX) {   // also false for u<=0 / NaN patterns with odd exponents
+    const int sub = (int)((b >> (52 - MP_DISC_NSUB_LOG2)) & ((1 << MP_DISC_NSUB_LOG2) - 1));
+    const double* row = &mp_disc_table[((e - MP_DISC_EMIN) << MP_DISC_NSUB_LOG2) + sub][0];
+    // mantissa in [1,2) -> local coordinate s in [-1,1)
+    const double m = bitsd((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    const double centre = 1.0 + (sub + 0.5) * (1.0 / (1 << MP_DISC_NSUB_LOG2));
+    const double s = (m - centre) * (double)(2 << MP_DISC_NSUB_LOG2);
+    // degree-10 polynomial, Estrin-style split into even/odd halves for ILP
+    const double s2 = s * s;
+    double ev = ldg(row + 10);
+    double od = ldg(row + 9);
+    ev = fma(ev, s2, ldg(row + 8));
+    od = fma(od, s2, ldg(row + 7));
+    ev = fma(ev, s2, ldg(row + 6));
+    od = fma(od, s2, ldg(row + 5));
+    ev = fma(ev, s2, ldg(row + 4));
+    od = fma(od, s2, ldg(row + 3));
+    ev = fma(ev, s2, ldg(row + 2));
+    od = fma(od, s2, ldg(row + 1));
+    ev = fma(ev, s2, ldg(row + 0));
+    return fma(od, s, ev);
+  }
+  if (!(u > 0.0)) return NAN;
+  if (e > MP_DISC_EMAX) {  // asymptotic series, u >= 2^22: next term 16/u^3 < 3e-19
+    const double iu = 1.0 / u;
+    const double c = cbrt(iu);
+    const double p = iu * c * c;  // u^(-5/3)
+    return p * fma(fma(40.0 / 9.0, iu, 5.0 / 3.0), iu, 1.0);
+  }
+  // convergent series, u < 2^-10: e^-u u^(-2/3) sum u^k / (k! (k-2/3))
+  const double c = cbrt(u);
+  double sum = 0.0, term = 1.0;
+  sum = -1.5;
+  for (int k = 1; k <= 6; ++k) {
+    term *= u / k;
+    sum += term / (k - 2.0 / 3.0);
+  }
+  return exp(-u) * sum / (c * c);
+}
+
+// ---- per-walker constants ---------------------------------------------------
+struct Walker {
+  // disc mass: M(t) = K*S(u) + C*exp(-(u-u0)), u = t*inv_tv + eps
+  double inv_tv, eps, u0, K, C, M_init;
+  // right-hand side
+  double A_rm;     // Rm(uncapped) = A_rm * M^(-2/7)
+  double Cw;       // w(uncapped)  = Cw * M^(-3/7) * omega
+  double Ccap;     // w(capped)    = Ccap / sqrt(omega)
+  double kc;       // k*c : capped when Rm*omega >= k*c
+  double Cdip_I;   // mu^2/(6c^3)/I
+  // luminosity stage (its own alpha/cs7/k/n may differ from the RHS's)
+  double l_inv_tv, l_A_rm, l_Cw, l_Ccap, l_kc;
+  double Ldip_coef;   // mu^2/(6 c^3)
+  double dipeff, propeff, f_beam;
+  double omega0;
+  int bad;         // non-finite / unphysical constants
+};
+
+MP_HD double pow_m17(double x) { return exp(log(x) * (-1.0 / 7.0)); }
+
+// pars = physical (B, P, MdiscI, RdiscI, epsilon, delta)
+MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, double propeff,
+                        double f_beam, double t_start, Walker& w) {
+  const double B = pars[0], P = pars[1], MdiscI = pars[2], RdiscI = pars[3];
+  const double epsilon = pars[4], delta = pars[5];
+  // init_conds: funcs.py:68-69
+  w.M_init = MdiscI * kMsol;
+  w.omega0 = kTwoPi / (1.0e-3 * P);
+  const double mu = 1.0e15 * B * (kR * kR * kR);
+  const double tv = RdiscI * sp.rhs_tv_per_R;
+  const double M0 = delta * MdiscI * kMsol;
+  w.inv_tv = 1.0 / tv;
+  w.eps = epsilon;
+  w.u0 = fma(t_start, w.inv_tv, epsilon);
+  const double ce = cbrt(epsilon);
+  w.K = M0 * ce * ce;
+  w.C = w.M_init - w.K * disc_S(w.u0);
+  const double mu47 = exp(log(mu) * (4.0 / 7.0));
+  const double gm17 = exp(log(kGM) * (-1.0 / 7.0));
+  const double base = mu47 * gm17;
+  w.A_rm = base * exp(log(sp.mdot_factor * w.inv_tv) * (-2.0 / 7.0));
+  w.Cw = w.A_rm * sqrt(w.A_rm) / sqrt(kGM);
+  w.kc = sp.rhs_k * kC;
+  w.Ccap = w.kc * sqrt(w.kc) / sqrt(kGM);
+  w.Ldip_coef = (mu * mu) / (6.0 * (kC * kC * kC));
+  w.Cdip_I = w.Ldip_coef * sp.inv_inertia;
+  const double ltv = RdiscI * sp.lum_tv_per_R;
+  w.l_inv_tv = 1.0 / ltv;
+  w.l_A_rm = base * exp(log(sp.mdot_factor * w.l_inv_tv) * (-2.0 / 7.0));
+  w.l_Cw = w.l_A_rm * sqrt(w.l_A_rm) / sqrt(kGM);
+  w.l_kc = sp.lum_k * kC;
+  w.l_Ccap = w.l_kc * sqrt(w.l_kc) / sqrt(kGM);
+  w.dipeff = dipeff;
+  w.propeff = propeff;
+  w.f_beam = f_beam;
+  const double probe = w.K + w.C + w.A_rm + w.Cw + w.omega0 + w.l_A_rm + w.inv_tv;
+  w.bad = !(isfinite(probe) && w.M_init > 0.0 && tv > 0.0 && ltv > 0.0 && epsilon > 0.0 &&
+            delta >= 0.0 && w.omega0 > 0.0 && mu > 0.0);
+}
+
+// Disc mass at time t (closed form of funcs.py:126-129).
+MP_HD double disc_mass(const Walker& w, double t) {
+  const double u = fma(t, w.inv_tv, w.eps);
+  const double S = disc_S(u);
+  const double E = exp(w.u0 - u);
+  return fma(w.K, S, w.C * E);
+}
+
+// Quantities of the RHS that depend on time only (through the disc mass).
+struct DiscAt {
+  double mdot;   // Mdisc/tvisc
+  double rm;     // uncapped Alfven radius
+  double wq;     // uncapped fastness / omega
+};
+
+MP_HD DiscAt disc_at(const Walker& w, double t) {
+  const double M = disc_mass(w, t);
+  const double q = pow_m17(M);
+  const double q2 = q * q;
+  DiscAt d;
+  d.mdot = M * w.inv_tv;
+  d.rm = w.A_rm * q2;
+  d.wq = w.Cw * q2 * q;
+  return d;
+}
+
+// d(omega)/dt: funcs.py:105-140 with the time-only factors hoisted into DiscAt.
+//   Rm/Rc = Rm * omega^(2/3) / GM^(1/3)  =>  w = (Rm/Rc)^(3/2) = Rm^(3/2) omega / sqrt(GM)
+//   capped (Rm >= k c/omega):            w = (k c)^(3/2) / sqrt(GM omega)
+//   Mdotacc - Mdotprop = (eta1 - eta2) Mdot = -tanh(n (w-1)) Mdot
+MP_HD double spin_rhs(const Spec& sp, const Walker& w, const DiscAt& d, double omega) {
+  double fast, rm;
+  if (d.rm * omega >= w.kc) {
+    rm = w.kc / omega;
+    fast = w.Ccap / sqrt(omega);
+  } else {
+    rm = d.rm;
+    fast = d.wq * omega;
+  }
+  const double om2 = omega * omega;
+  double nacc = 0.0;
+  if (!(om2 > sp.omega2_breakup_rhs)) {
+    const double th = tanh(sp.rhs_n * (fast - 1.0));
+    const double lever = (rm >= kR) ? sqrt(kGM * rm) : sp.sqrt_GMR;
+    nacc = -lever * d.mdot * th;
+  }
+  return fma(-w.Cdip_I * om2, omega, nacc * sp.inv_inertia);
+}
+
+// Luminosity stage at one node (erg/s, not yet /1e50): funcs.py:175-229.
+struct Lum { double tot, prop, dip; };
+
+MP_HD Lum luminosity(const Spec& sp, const Walker& w, double M, double omega) {
+  const double q = pow_m17(M);
+  const double q2 = q * q;
+  const double mdot = M * w.l_inv_tv;
+  double rm = w.l_A_rm * q2;
+  double fast;
+  if (rm * omega >= w.l_kc) {       // Rm >= k*Rlc  (funcs.py:189-190)
+    rm = w.l_kc / omega;
+    fast = w.l_Ccap / sqrt(omega);
+  } else {
+    fast = w.l_Cw * q2 * q * omega;
+  }
+  const double om2 = omega * omega;
+  const double th = tanh(sp.lum_n * (fast - 1.0));
+  const double eta2 = 0.5 * (1.0 + th);
+  const double eta1 = 1.0 - eta2;
+  const double mprop = eta2 * mdot, macc = eta1 * mdot;
+  double nacc;
+  if (om2 > sp.omega2_breakup_lum) {
+    nacc = 0.0;
+  } else {
+    const double lever = (rm >= kR) ? sqrt(kGM * rm) : sp.sqrt_GMR;
+    nacc = lever * (macc - mprop);
+  }
+  double ldip = w.dipeff * (w.Ldip_coef * (om2 * om2));
+  if (ldip <= 0.0 || !isfinite(ldip)) ldip = 0.0;                      // funcs.py:216-219
+  double lprop = -1.0 * nacc * omega;
+  if (sp.lprop_binding_term) lprop -= (kGM / rm) * eta2 * mdot;        // funcs.py:222-223
+  lprop *= w.propeff;
+  if (lprop <= 0.0 || !isfinite(lprop)) lprop = 0.0;                   // funcs.py:224-227
+  Lum L;
+  L.dip = ldip;
+  L.prop = lprop;
+  L.tot = w.f_beam * (ldip + lprop);                                   // funcs.py:229
+  return L;
+}
+
+// ---- Dormand-Prince 5(4) with dense output --------------------------------
+struct Dopri {
+  // coefficients (Dormand & Prince 1980; dense output of Hairer, Norsett & Wanner II.6)
+  static constexpr double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
+  static constexpr double a21 = 1.0 / 5;
+  static constexpr double a31 = 3.0 / 40, a32 = 9.0 / 40;
+  static constexpr double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
+  static constexpr double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
+  static constexpr double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656;
+  static constexpr double a71 = 35.0 / 384, a73 = 500.0 / 1113, a74 = 125.0 / 192, a75 = -2187.0 / 6784, a76 = 11.0 / 84;
+  static constexpr double e1 = 71.0 / 57600, e3 = -71.0 / 16695, e4 = 71.0 / 1920, e5 = -17253.0 / 339200, e6 = 22.0 / 525, e7 = -1.0 / 40;
+  static constexpr double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0,
+                          d4 = -10690763975.0 / 1880347072.0, d5 = 701980252875.0 / 199316789632.0,
+                          d6 = -1453857185.0 / 822651844.0, d7 = 69997945.0 / 29380423.0;
+};
+
+// State of the spin integration of one walker.
+struct Integrator {
+  double t, omega, h, k1;        // k1 = f(t, omega) (FSAL)
+  double facold;
+  int rejected;                  // previous attempt was rejected
+  // dense output of the last accepted step: omega(t0 + theta*hs)
+  double t0, hs, r1, r2, r3, r4, r5, t1;
+  int n_rhs, n_steps, status;
+};
+
+MP_HD double dense_eval(const Integrator& in, double tq) {
+  const double th = (tq - in.t0) / in.hs;
+  const double th1 = 1.0 - th;
+  return fma(th, fma(th1, fma(th, fma(th1, in.r5, in.r4), in.r3), in.r2), in.r1);
+}
+
+MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, double t_end,
+                           Integrator& in) {
+  in.t = t_start;
+  in.omega = w.omega0;
+  in.facold = 1.0e-4;
+  in.rejected = 0;
+  in.n_steps = 0;
+  in.status = kWalkerOk;
+  in.t0 = t_start; in.t1 = t_start; in.hs = 1.0;
+  in.r1 = w.omega0; in.r2 = in.r3 = in.r4 = in.r5 = 0.0;
+  const DiscAt d0 = disc_at(w, t_start);
+  in.k1 = spin_rhs(sp, w, d0, in.omega);
+  // initial step (Hairer's hinit, order 5)
+  const double sk = sp.rtol * fabs(in.omega);
+  const double dnf = fabs(in.k1) / sk, dny = fabs(in.omega) / sk;
+  double h = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : 0.01 * (dny / dnf);
+  const double span = t_end - t_start;
+  h = fmin(h, span);
+  const double y1 = fma(h, in.k1, in.omega);
+  const DiscAt d1 = disc_at(w, t_start + h);
+  const double f1 = spin_rhs(sp, w, d1, y1);
+  const double der2 = fabs(f1 - in.k1) / sk / h;
+  const double der12 = fmax(der2, dnf);
+  const double h1 = (der12 <= 1e-15) ? fmax(1.0e-6, fabs(h) * 1.0e-3)
+                                     : exp(log(0.01 / der12) * 0.2);
+  in.h = fmin(fmin(100.0 * h, h1), span);
+  in.n_rhs = 2;
+  if (!(isfinite(in.k1) && isfinite(in.h) && in.h > 0.0)) in.status = kWalkerIntegratorFail;
+}
+
+// Attempt one step; on acceptance advances (t, omega) and refreshes the dense
+// output.  Returns true when a step was accepted.
+MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
+  using D = Dopri;
+  const double t = in.t, y = in.omega;
+  double h = in.h;
+  bool last = false;
+  if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
+  const double k1 = in.k1;
+  const DiscAt m2 = disc_at(w, fma(D::c2, h, t));
+  const double k2 = spin_rhs(sp, w, m2, fma(h, D::a21 * k1, y));
+  const DiscAt m3 = disc_at(w, fma(D::c3, h, t));
+  const double k3 = spin_rhs(sp, w, m3, fma(h, fma(D::a32, k2, D::a31 * k1), y));
+  const DiscAt m4 = disc_at(w, fma(D::c4, h, t));
+  const double k4 = spin_rhs(sp, w, m4, fma(h, fma(D::a43, k3, fma(D::a42, k2, D::a41 * k1)), y));
+  const DiscAt m5 = disc_at(w, fma(D::c5, h, t));
+  const double k5 = spin_rhs(sp, w, m5, fma(h, fma(D::a54, k4, fma(D::a53, k3, fma(D::a52, k2, D::a51 * k1))), y));
+  const double tn = last ? t_end : t + h;
+  const DiscAt m6 = disc_at(w, tn);
+  const double k6 = spin_rhs(sp, w, m6, fma(h, fma(D::a65, k5, fma(D::a64, k4, fma(D::a63, k3, fma(D::a62, k2, D::a61 * k1)))), y));
+  const double ynew = fma(h, fma(D::a76, k6, fma(D::a75, k5, fma(D::a74, k4, fma(D::a73, k3, D::a71 * k1)))), y);
+  const double k7 = spin_rhs(sp, w, m6, ynew);
+  in.n_rhs += 6;
+  const double errv = h * fma(D::e7, k7, fma(D::e6, k6, fma(D::e5, k5, fma(D::e4, k4, fma(D::e3, k3, D::e1 * k1)))));
+  const double sk = sp.rtol * fmax(fabs(y), fabs(ynew));
+  double err = fabs(errv) / sk;
+  if (!(err == err)) err = 1.0e10;            // NaN => reject and shrink
+  // PI controller (beta = 0.04), Hairer dopri5 defaults
+  const double beta = 0.04, expo1 = 0.2 - beta * 0.75, safe = 0.9, facc1 = 1.0 / 0.2, facc2 = 1.0 / 10.0;
+  const double fac11 = (err > 0.0) ? exp(log(err) * expo1) : 0.0;
+  double fac = fac11 * exp(-log(in.facold) * beta);
+  fac = fmax(facc2, fmin(facc1, fac / safe));
+  double hnew = h / fac;
+  if (err <= 1.0) {
+    in.facold = fmax(err, 1.0e-4);
+    // dense output
+    const double ydiff = ynew - y;
+    const double bspl = fma(h, k1, -ydiff);
+    in.r1 = y;
+    in.r2 = ydiff;
+    in.r3 = bspl;
+    in.r4 = ydiff - h * k7 - bspl;
+    in.r5 = h * fma(D::d7, k7, fma(D::d6, k6, fma(D::d5, k5, fma(D::d4, k4, fma(D::d3, k3, D::d1 * k1)))));
+    in.t0 = t; in.hs = h; in.t1 = tn;
+    in.t = tn;
+    in.omega = ynew;
+    in.k1 = k7;
+    in.h = in.rejected ? fmin(hnew, h) : hnew;
+    in.rejected = 0;
+    in.n_steps++;
+    return true;
+  }
+  // rejected
+  hnew = h / fmin(facc1, fac11 / safe);
+  in.h = hnew;
+  in.rejected = 1;
+  in.n_steps++;
+  if (!(fabs(hnew) > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
+  return false;
+}
+
+// ---- parameter handling -------------------------------------------------------
+// theta (as the sampler holds it) -> prior test + physical parameters.
+// Returns false when the prior rejects (mcmc_eqns.py:43-49: inclusive, NaN rejects).
+MP_HD bool prior_accepts(const double* theta, int ndim, const double* lower, const double* upper) {
+  bool ok = true;
+  for (int i = 0; i < ndim; ++i) ok = ok && (theta[i] <= upper[i]) && (theta[i] >= lower[i]);
+  return ok;
+}
+
+MP_HD double exp10_ref(double x) {
+  // 10.0 ** x as NumPy computes it (libm pow); CUDA's pow is <= 2 ulp
+  return pow(10.0, x);
+}
+
+// theta -> (physical parameters, efficiencies) per the reference's lnlike:
+//   script   mcmc_eqns.py:16-17   arr[2:] = 10 ** arr[2:]   (unlog_mask bits 2..5)
+//   packaged magnetar/mcmc_eqns.py:22-34   7: f_beam; 8: dipeff, propeff; 9: all three
+MP_HD void unpack_theta(const Spec& sp, const double* theta, int ndim, double* pars, double& dipeff,
+                        double& propeff, double& f_beam) {
+  for (int i = 0; i < 6; ++i) pars[i] = ((sp.unlog_mask >> i) & 1) ? exp10_ref(theta[i]) : theta[i];
+  dipeff = sp.dipeff;
+  propeff = sp.propeff;
+  f_beam = sp.f_beam;
+  if (ndim == 7) {
+    f_beam = theta[6];
+  } else if (ndim == 8) {
+    dipeff = theta[6];
+    propeff = theta[7];
+  } else if (ndim == 9) {
+    dipeff = theta[6];
+    propeff = theta[7];
+    f_beam = theta[8];
+  }
+}
+
+
+// ---- one walker, end to end -----------------------------------------------------
+enum EvalMode { kModeLnprob = 0, kModeModelAtData = 1, kModeCurves = 2 };
+
+// Integrates the spin equation across the nodes of `dv`, NB nodes at a time:
+//   phase A  advance the integrator, dropping omega(node) from the dense output
+//            into buf[(j - c0) * bstride]            (divergent, but tiny)
+//   phase B  luminosity at the buffered nodes, interpolation onto the data and
+//            chi-square / model output               (converged across a warp:
+//            every lane walks the same node and datum indices)
+// Returns chi-square (kModeLnprob).  out/state_out semantics per mode:
+//   kModeModelAtData : out[dat_orig[i]*ostride] = model at sorted datum i (/1e50)
+//   kModeCurves      : out[(c*Gs + j)*ostride]  = Ltot,Lprop,Ldip (c=0,1,2) at node j (/1e50)
+//                      state_out[(c*Gs + j)*ostride] = Mdisc, omega (optional)
+template <int MODE, int NB>
+MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w, double* buf,
+                             int bstride, int& status, int& n_rhs, double* out,
+                             double* state_out, int ostride, const int* dat_orig) {
+  const int Nn = dv.n_nodes;
+  n_rhs = 0;
+  if (Nn <= 0) return 0.0;
+  const double t_end = ldg(dv.node_t + (Nn - 1));
+  Integrator in;
+  in.status = kWalkerOk;
+  in.n_rhs = 0;
+  if (w.bad) {
+    status |= kWalkerNonfiniteState;
+  } else {
+    integrator_init(sp, w, dv.t_start, t_end, in);
+  }
+  int jn = 0, idat = 0;
+  double chi2 = 0.0, Lprev = 0.0;
+  for (int c0 = 0; c0 < Nn; c0 += NB) {
+    const int c1 = (c0 + NB < Nn) ? c0 + NB : Nn;
+    // ---- phase A
+    if (w.bad) {
+      for (; jn < c1; ++jn)
+        buf[(jn - c0) * bstride] = (ldg(dv.node_t + jn) == dv.t_start) ? w.omega0 : NAN;
+    } else {
+      while (jn < c1) {
+        const double tn = ldg(dv.node_t + jn);
+        if (tn <= in.t1) {
+          buf[(jn - c0) * bstride] = dense_eval(in, tn);
+          ++jn;
+        } else if (in.status != kWalkerOk) {
+          buf[(jn - c0) * bstride] = NAN;
+          ++jn;
+        } else {
+          integrator_step(sp, w, t_end, in);
+        }
+      }
+    }
+    // ---- phase B
+    for (int j = c0; j < c1; ++j) {
+      const double om = buf[(j - c0) * bstride];
+      const double tn = ldg(dv.node_t + j);
+      double M;
+      if (w.bad) M = (tn == dv.t_start) ? w.M_init : NAN;
+      else M = disc_mass(w, tn);
+      const Lum L = luminosity(sp, w, M, om);
+      if (MODE == kModeCurves) {
+        out[(0 * Nn + j) * ostride] = L.tot / 1.0e50;
+        out[(1 * Nn + j) * ostride] = L.prop / 1.0e50;
+        out[(2 * Nn + j) * ostride] = L.dip / 1.0e50;
+        if (state_out) {
+          state_out[(0 * Nn + j) * ostride] = M;
+          state_out[(1 * Nn + j) * ostride] = om;
+        }
+      } else {
+        while (idat < dv.n_data) {
+          const int lo = dv.dat_lo[idat];
+          const double dx = ldg(dv.dat_dx + idat);
+          const int hi = lo + (dx != 0.0 ? 1 : 0);
+          if (hi > j) break;
+          double mod;
+          if (dx == 0.0) {
+            mod = L.tot;                                   // datum sits on a grid node
+          } else {
+            const double slope = (L.tot - Lprev) / ldg(dv.dat_Dx + idat);
+            mod = fma(slope, dx, Lprev);                   // np.interp: slope*(x-x_lo)+y_lo
+          }
+          mod /= 1.0e50;
+          if (MODE == kModeLnprob) {
+            const double r = (ldg(dv.dat_y + idat) - mod) / ldg(dv.dat_yerr + idat);
+            chi2 = fma(r, r, chi2);
+          } else {
+            out[(dat_orig ? dat_orig[idat] : idat) * ostride] = mod;
+          }
+          ++idat;
+        }
+        Lprev = L.tot;
+      }
+    }
+  }
+  status |= in.status;
+  n_rhs = in.n_rhs;
+  return chi2;
+}
+
+}  // namespace mp

@@ -1,0 +1,108 @@
+// magprop_host.hpp -- host-side preparation shared by the CUDA library and the
+// test-only host simulator: mp_model_spec -> mp::Spec, and the "node program"
+// that tells the kernel which grid nodes a dataset needs.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+#include "../../include/magprop_b200.h"
+#include "magprop_core.cuh"
+
+namespace mp {
+
+inline Spec make_spec(const mp_model_spec& m) {
+  Spec s;
+  s.inertia = m.inertia_factor * kM * (kR * kR);        // funcs.py:17 / magnetar/funcs.py:12
+  s.inv_inertia = 1.0 / s.inertia;
+  s.mdot_factor = m.mdot_factor;
+  s.rhs_n = m.rhs_n;
+  s.rhs_tv_per_R = 1.0e5 / (m.rhs_alpha * m.rhs_cs7 * 1.0e7);   // funcs.py:98-99
+  s.rhs_k = m.rhs_k;
+  s.lum_n = m.lum_n;
+  s.lum_tv_per_R = 1.0e5 / (m.lum_alpha * m.lum_cs7 * 1.0e7);   // funcs.py:182-183
+  s.lum_k = m.lum_k;
+  s.dipeff = m.dipeff;
+  s.propeff = m.propeff;
+  s.f_beam = m.f_beam;
+  // rot_param = 0.5 I w^2 / |W| > b   <=>   w^2 > b |W| / (0.5 I)      (funcs.py:113-116,131)
+  const double x = kGM / (kR * (kC * kC));
+  const double modW = 0.6 * kM * (kC * kC) * (x / (1.0 - 0.5 * x));
+  s.omega2_breakup_rhs = m.breakup_rhs * modW / (0.5 * s.inertia);
+  s.omega2_breakup_lum = m.breakup_lum * modW / (0.5 * s.inertia);
+  s.sqrt_GMR = std::sqrt(kGM * kR);
+  s.lprop_binding_term = m.lprop_binding_term;
+  s.unlog_mask = m.unlog_mask;
+  s.rtol = (m.rtol > 0.0) ? m.rtol : 1.0e-10;
+  s.max_steps = (m.max_steps > 0) ? m.max_steps : 200000;
+  return s;
+}
+
+// Which grid nodes a dataset touches, and how each datum interpolates between
+// them.  Mirrors interp1d(tarr, Ltot)(xdata) (funcs.py:233-234): linear between
+// the bracketing nodes; a datum equal to a node takes that node's value; a datum
+// outside [grid[0], grid[G-1]] is an error (bounds_error=True).
+struct NodeProgram {
+  std::vector<double> node_t;          // unique nodes, ascending
+  std::vector<int> node_grid_index;    // their indices in the grid
+  std::vector<double> y, yerr, dx, Dx; // data sorted by time
+  std::vector<int> lo;                 // index into node_t
+  std::vector<int> order;              // sorted position -> original index
+};
+
+inline int build_node_program(const double* grid, int G, const double* t, const double* y,
+                              const double* yerr, int D, NodeProgram& np) {
+  if (G < 2) return MP_ERR_BAD_GRID;
+  for (int i = 1; i < G; ++i)
+    if (!(grid[i] > grid[i - 1])) return MP_ERR_BAD_GRID;
+  np = NodeProgram();
+  np.order.resize(D);
+  std::iota(np.order.begin(), np.order.end(), 0);
+  for (int i = 0; i < D; ++i)
+    if (!(t[i] >= grid[0] && t[i] <= grid[G - 1])) return MP_ERR_DATA_RANGE;  // also NaN
+  std::stable_sort(np.order.begin(), np.order.end(), [&](int a, int b) { return t[a] < t[b]; });
+  std::vector<int> glo(D), need_hi(D);
+  std::vector<int> nodes;
+  for (int s = 0; s < D; ++s) {
+    const double x = t[np.order[s]];
+    // largest j with grid[j] <= x
+    int j = int(std::upper_bound(grid, grid + G, x) - grid) - 1;
+    glo[s] = j;
+    need_hi[s] = (x != grid[j]);
+    nodes.push_back(j);
+    if (need_hi[s]) nodes.push_back(j + 1);
+  }
+  std::sort(nodes.begin(), nodes.end());
+  nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+  np.node_grid_index = nodes;
+  for (int j : nodes) np.node_t.push_back(grid[j]);
+  for (int s = 0; s < D; ++s) {
+    const int o = np.order[s];
+    const int li = int(std::lower_bound(nodes.begin(), nodes.end(), glo[s]) - nodes.begin());
+    np.lo.push_back(li);
+    np.y.push_back(y[o]);
+    np.yerr.push_back(yerr[o]);
+    if (need_hi[s]) {
+      np.dx.push_back(t[o] - grid[glo[s]]);
+      np.Dx.push_back(grid[glo[s] + 1] - grid[glo[s]]);
+    } else {
+      np.dx.push_back(0.0);
+      np.Dx.push_back(1.0);
+    }
+  }
+  return MP_OK;
+}
+
+// Nodes of a full-curve evaluation: every stride-th grid node plus the last.
+inline void build_curve_nodes(const double* grid, int G, int stride, std::vector<double>& node_t,
+                              std::vector<int>& node_grid_index) {
+  node_t.clear();
+  node_grid_index.clear();
+  if (stride < 1) stride = 1;
+  for (int j = 0; j < G; j += stride) node_grid_index.push_back(j);
+  if (node_grid_index.back() != G - 1) node_grid_index.push_back(G - 1);
+  for (int j : node_grid_index) node_t.push_back(grid[j]);
+}
+
+}  // namespace mp

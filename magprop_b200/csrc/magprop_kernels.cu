@@ -1,0 +1,647 @@
+// magprop_kernels.cu -- sm_100a kernels and the C ABI of include/magprop_b200.h.
+//
+// Kernels (one walker per thread, FP64 throughout, no tensor cores -- the path
+// is a scalar ODE solve, not a contraction):
+//   eval_kernel<kModeLnprob>      prior -> spin ODE -> luminosity -> interp -> chi2 -> lnprob
+//   eval_kernel<kModeModelAtData> same, writes the model at the data times
+//   eval_kernel<kModeCurves>      same, writes Ltot/Lprop/Ldip (and state) at grid nodes
+//   stretch_kernel                emcee stretch-move proposal + the above + accept, fused
+//   rhs_kernel                    the coupled reference RHS for ODEs()/odes() callers
+//   dfma_peak_kernel              FP64 FMA roofline denominator
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "magprop_host.hpp"
+
+namespace mp {
+
+constexpr int kNB = 32;  // nodes buffered per thread between phase A and phase B
+
+struct KernelArgs {
+  Spec sp;
+  DataView dv;
+  const int* dat_orig;  // sorted datum -> caller's index (kModeModelAtData)
+  double lower[MP_MAX_NDIM], upper[MP_MAX_NDIM];
+  int prior_enabled;
+  int ndim;
+  int W;
+  const double* theta;  // [W][ndim]
+  double* lnp;          // [W]
+  int* status;          // [W] or null
+  int* n_rhs;           // [W] or null
+  double* out;          // mode-dependent
+  double* state;        // curves: [W][2][Gs] or null
+};
+
+// Coalesced load of this block's walker parameters into shared memory
+// (theta rows are 48..72 B apart, so per-thread row reads would be 8-byte
+// gathers).
+template <int BLOCK>
+__device__ __forceinline__ void stage_theta(const double* __restrict__ theta, int W, int ndim,
+                                            double* s_theta) {
+  const long long base = (long long)blockIdx.x * BLOCK * ndim;
+  const long long total = (long long)W * ndim;
+  for (int i = threadIdx.x; i < BLOCK * ndim; i += BLOCK) {
+    const long long g = base + i;
+    s_theta[i] = (g < total) ? theta[g] : 0.0;
+  }
+  __syncthreads();
+}
+
+template <int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) eval_kernel(const __grid_constant__ KernelArgs a) {
+  __shared__ double s_buf[kNB * BLOCK];
+  __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
+  stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta);
+  const int w = blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= a.W) return;
+  const double* th = s_theta + threadIdx.x * a.ndim;
+
+  int st = kWalkerOk, nr = 0;
+  double result = -INFINITY;
+  if (a.prior_enabled && !prior_accepts(th, a.ndim, a.lower, a.upper)) {
+    st = kWalkerPriorReject;                       // mcmc_eqns.py:66-69: model is skipped
+  } else {
+    double pars[6], dipeff, propeff, f_beam;
+    unpack_theta(a.sp, th, a.ndim, pars, dipeff, propeff, f_beam);
+    Walker wk;
+    walker_setup(a.sp, pars, dipeff, propeff, f_beam, a.dv.t_start, wk);
+    double* out = nullptr;
+    double* state = nullptr;
+    if (MODE == kModeCurves) {
+      out = a.out + (size_t)w * 3 * a.dv.n_nodes;
+      state = a.state ? a.state + (size_t)w * 2 * a.dv.n_nodes : nullptr;
+    } else if (MODE == kModeModelAtData) {
+      out = a.out + (size_t)w * a.dv.n_data;
+    }
+    const double chi2 = evaluate_walker<MODE, kNB>(a.sp, a.dv, wk, s_buf + threadIdx.x, BLOCK, st, nr,
+                                                   out, state, 1, a.dat_orig);
+    if (MODE == kModeLnprob) {
+      double ll = -0.5 * chi2;                     // mcmc_eqns.py:25
+      if (st & kWalkerIntegratorFail) {
+        ll = -INFINITY;                            // 'flag' -> -inf (mcmc_eqns.py:22-23)
+      } else if (!isfinite(ll)) {
+        st |= kWalkerNonfiniteLnlike;              // mcmc_eqns.py:72-79
+        ll = -INFINITY;
+      }
+      result = ll;                                 // + lnprior == 0.0
+    }
+  }
+  if (MODE == kModeLnprob) a.lnp[w] = result;
+  if (a.status) a.status[w] = st;
+  if (a.n_rhs) a.n_rhs[w] = nr;
+}
+
+// ---- counter-based RNG: Philox4x32-10 (Salmon et al. 2011) -------------------
+struct Philox {
+  uint32_t c[4];
+};
+__host__ __device__ inline Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox o;
+  o.c[0] = c0; o.c[1] = c1; o.c[2] = c2; o.c[3] = c3;
+  return o;
+}
+// 53-bit uniform in (0,1): never 0 so log() is finite
+__host__ __device__ inline double u01(uint32_t hi, uint32_t lo) {
+  const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
+  return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+struct StretchArgs {
+  KernelArgs k;          // k.theta unused; k.lnp unused
+  double* coords;        // [nwalkers][ndim], updated in place
+  double* lnp;           // [nwalkers]
+  const int* active;     // [n_active] walkers to move (disjoint from complement)
+  const int* complement; // [n_complement]
+  int n_active, n_complement;
+  double a;
+  uint64_t seed, step;
+  int* accepted;         // [nwalkers] counters (may be null)
+};
+
+// One emcee StretchMove half-step (Goodman & Weare 2010; emcee RedBlueMove):
+//   z = ((a-1) u + 1)^2 / a ; q = c - (c - s) z ; accept iff (ndim-1) ln z + lp(q) - lp(s) > ln u'
+// fused with the likelihood so a half-step is one launch.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) stretch_kernel(const __grid_constant__ StretchArgs s) {
+  __shared__ double s_buf[kNB * BLOCK];
+  const KernelArgs& a = s.k;
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= s.n_active) return;
+  const int me = s.active[i];
+  const int ndim = a.ndim;
+  // counter = (step, walker); two Philox blocks give u_z, u_partner, u_accept
+  const Philox r0 = philox4x32_10((uint32_t)s.step, (uint32_t)(s.step >> 32), (uint32_t)me, 0u,
+                                  (uint32_t)s.seed, (uint32_t)(s.seed >> 32));
+  const Philox r1 = philox4x32_10((uint32_t)s.step, (uint32_t)(s.step >> 32), (uint32_t)me, 1u,
+                                  (uint32_t)s.seed, (uint32_t)(s.seed >> 32));
+  const double uz = u01(r0.c[0], r0.c[1]);
+  const double up = u01(r0.c[2], r0.c[3]);
+  const double ua = u01(r1.c[0], r1.c[1]);
+  const double zr = (s.a - 1.0) * uz + 1.0;
+  const double z = zr * zr / s.a;
+  int pj = (int)(up * s.n_complement);
+  if (pj >= s.n_complement) pj = s.n_complement - 1;
+  const int partner = s.complement[pj];
+  double q[MP_MAX_NDIM];
+  for (int d = 0; d < ndim; ++d) {
+    const double c = s.coords[(size_t)partner * ndim + d];
+    const double x = s.coords[(size_t)me * ndim + d];
+    q[d] = c - (c - x) * z;
+  }
+  int st = kWalkerOk, nr = 0;
+  double lp_new = -INFINITY;
+  if (!a.prior_enabled || prior_accepts(q, ndim, a.lower, a.upper)) {
+    double pars[6], dipeff, propeff, f_beam;
+    unpack_theta(a.sp, q, ndim, pars, dipeff, propeff, f_beam);
+    Walker wk;
+    walker_setup(a.sp, pars, dipeff, propeff, f_beam, a.dv.t_start, wk);
+    const double chi2 = evaluate_walker<kModeLnprob, kNB>(a.sp, a.dv, wk, s_buf + threadIdx.x, BLOCK, st,
+                                                          nr, nullptr, nullptr, 1, nullptr);
+    double ll = -0.5 * chi2;
+    if ((st & kWalkerIntegratorFail) || !isfinite(ll)) ll = -INFINITY;
+    lp_new = ll;
+  }
+  const double lp_old = s.lnp[me];
+  const double lnpdiff = (ndim - 1.0) * log(z) + lp_new - lp_old;
+  if (lnpdiff > log(ua)) {
+    for (int d = 0; d < ndim; ++d) s.coords[(size_t)me * ndim + d] = q[d];
+    s.lnp[me] = lp_new;
+    if (s.accepted) s.accepted[me] += 1;
+  }
+  if (a.n_rhs) a.n_rhs[me] = nr;
+}
+
+// ---- the coupled right-hand side, as ODEs()/odes() return it -----------------------
+// funcs.py:75-142 / magnetar/funcs.py:33-101, operation order kept.
+__global__ void rhs_kernel(double inertia_factor, double mdot_factor, double breakup,
+                           const double* __restrict__ y, const double* __restrict__ t,
+                           const double* __restrict__ pars, double n, double alpha, double cs7, double k,
+                           int W, double* __restrict__ dydt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const double Mdisc = y[2 * i], omega = y[2 * i + 1], tt = t[i];
+  const double B = pars[5 * i], MdiscI = pars[5 * i + 1], RdiscI = pars[5 * i + 2];
+  const double epsilon = pars[5 * i + 3], delta = pars[5 * i + 4];
+  const double inertia = inertia_factor * kM * (kR * kR);
+  const double Rdisc = RdiscI * 1.0e5;
+  const double tvisc = Rdisc / (alpha * cs7 * 1.0e7);
+  const double mu = 1.0e15 * B * (kR * kR * kR);
+  const double M0 = delta * MdiscI * kMsol;
+  const double tfb = epsilon * tvisc;
+  double Rm = pow(mu, 4.0 / 7.0) * pow(kGM, -1.0 / 7.0) * pow((mdot_factor * Mdisc) / tvisc, -2.0 / 7.0);
+  const double Rc = pow(kGM / (omega * omega), 1.0 / 3.0);
+  const double Rlc = kC / omega;
+  if (Rm >= k * Rlc) Rm = k * Rlc;
+  const double w = pow(Rm / Rc, 1.5);
+  const double x = kGM / (kR * (kC * kC));
+  const double modW = 0.6 * kM * (kC * kC) * (x / (1.0 - 0.5 * x));
+  const double rot_param = (0.5 * inertia * (omega * omega)) / modW;
+  const double Ndip = (-1.0 * (mu * mu) * (omega * omega * omega)) / (6.0 * (kC * kC * kC));
+  const double eta2 = 0.5 * (1.0 + tanh(n * (w - 1.0)));
+  const double eta1 = 1.0 - eta2;
+  const double Mdotprop = eta2 * (Mdisc / tvisc);
+  const double Mdotacc = eta1 * (Mdisc / tvisc);
+  const double Mdotfb = (M0 / tfb) * pow((tt + tfb) / tfb, -5.0 / 3.0);
+  double Nacc;
+  if (rot_param > breakup) Nacc = 0.0;
+  else if (Rm >= kR) Nacc = sqrt(kGM * Rm) * (Mdotacc - Mdotprop);
+  else Nacc = sqrt(kGM * kR) * (Mdotacc - Mdotprop);
+  dydt[2 * i] = Mdotfb - Mdotacc - Mdotprop;
+  dydt[2 * i + 1] = (Nacc + Ndip) / inertia;
+}
+
+// ---- FP64 FMA peak: 8 independent chains per thread, 2 flop per DFMA ---------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 0.9999999, c = 1e-9;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+  if (s == 12345.678) out[0] = s;  // keep the chains alive
+}
+
+}  // namespace mp
+
+// =====================================================================================
+//                                     C ABI
+// =====================================================================================
+using namespace mp;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define MP_CUDA(call)                                                                     \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(MP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+struct DeviceNodes {
+  double* node_t = nullptr;
+  int n_nodes = 0;
+};
+
+struct mp_handle {
+  int device = 0;
+  mp_model_spec model;
+  Spec spec;
+  mp_prior_spec prior;
+  std::vector<double> grid;
+  // data
+  int D = 0;
+  NodeProgram np;
+  DeviceNodes data_nodes;
+  double *d_y = nullptr, *d_yerr = nullptr, *d_dx = nullptr, *d_Dx = nullptr;
+  int *d_lo = nullptr, *d_orig = nullptr;
+  // curve node sets per stride
+  std::map<int, DeviceNodes> curve_nodes;
+  // staging for the host-pointer entry points
+  double *s_theta = nullptr, *s_out = nullptr, *s_state = nullptr, *s_lnp = nullptr;
+  int *s_status = nullptr, *s_nrhs = nullptr;
+  size_t cap_theta = 0, cap_out = 0, cap_state = 0, cap_w = 0;
+  cudaStream_t stream = nullptr;
+};
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& v) {
+  *dst = nullptr;
+  if (v.empty()) return MP_OK;
+  MP_CUDA(cudaMalloc((void**)dst, v.size() * sizeof(T)));
+  MP_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return MP_OK;
+}
+
+template <typename T>
+static int ensure(T** p, size_t* cap, size_t need) {
+  if (need <= *cap) return MP_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  MP_CUDA(cudaMalloc((void**)p, need * sizeof(T)));
+  *cap = need;
+  return MP_OK;
+}
+
+extern "C" int mp_abi_version(void) { return MP_ABI_VERSION; }
+
+extern "C" int mp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" const char* mp_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mp_create(const mp_model_spec* spec, const mp_prior_spec* prior, const double* grid,
+                         int32_t G, const double* t, const double* y, const double* yerr, int32_t D,
+                         int32_t device, mp_handle** out) {
+  if (!spec || !grid || !out || D < 0 || (D > 0 && (!t || !y || !yerr)))
+    return fail(MP_ERR_BAD_ARG, "mp_create: null pointer or negative size");
+  *out = nullptr;
+  NodeProgram np;
+  int rc = build_node_program(grid, G, t, y, yerr, D, np);
+  if (rc == MP_ERR_BAD_GRID) return fail(rc, "mp_create: grid must be strictly increasing with >= 2 nodes");
+  if (rc == MP_ERR_DATA_RANGE)
+    return fail(rc, "A value in x_new is outside the interpolation range.");
+  if (mp_device_count() <= device || device < 0)
+    return fail(MP_ERR_CUDA, "mp_create: no such CUDA device (magprop_b200 has no CPU path)");
+  MP_CUDA(cudaSetDevice(device));
+  mp_handle* h = new mp_handle();
+  h->device = device;
+  h->model = *spec;
+  h->spec = make_spec(*spec);
+  if (prior) h->prior = *prior;
+  else std::memset(&h->prior, 0, sizeof(h->prior));
+  h->grid.assign(grid, grid + G);
+  h->D = D;
+  h->np = np;
+  h->data_nodes.n_nodes = (int)np.node_t.size();
+  if ((rc = upload(&h->data_nodes.node_t, np.node_t)) || (rc = upload(&h->d_y, np.y)) ||
+      (rc = upload(&h->d_yerr, np.yerr)) || (rc = upload(&h->d_dx, np.dx)) ||
+      (rc = upload(&h->d_Dx, np.Dx)) || (rc = upload(&h->d_lo, np.lo)) ||
+      (rc = upload(&h->d_orig, np.order))) {
+    mp_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return MP_OK;
+}
+
+extern "C" void mp_destroy(mp_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree(h->data_nodes.node_t);
+  cudaFree(h->d_y); cudaFree(h->d_yerr); cudaFree(h->d_dx); cudaFree(h->d_Dx);
+  cudaFree(h->d_lo); cudaFree(h->d_orig);
+  for (auto& kv : h->curve_nodes) cudaFree(kv.second.node_t);
+  cudaFree(h->s_theta); cudaFree(h->s_out); cudaFree(h->s_state); cudaFree(h->s_lnp);
+  cudaFree(h->s_status); cudaFree(h->s_nrhs);
+  delete h;
+}
+
+extern "C" int mp_set_prior(mp_handle* h, const mp_prior_spec* prior) {
+  if (!h || !prior) return fail(MP_ERR_BAD_ARG, "mp_set_prior: null pointer");
+  h->prior = *prior;
+  return MP_OK;
+}
+
+static int fill_args(mp_handle* h, KernelArgs& a, const DeviceNodes& nodes, bool with_data, int ndim, int W,
+                     bool use_prior) {
+  if (ndim < 6 || ndim > MP_MAX_NDIM) return fail(MP_ERR_BAD_ARG, "ndim must be 6, 7, 8 or 9");
+  if (W < 0) return fail(MP_ERR_BAD_ARG, "negative walker count");
+  if (use_prior && h->prior.enabled && h->prior.ndim != ndim)
+    return fail(MP_ERR_BAD_ARG, "prior dimension does not match ndim");
+  std::memset(&a, 0, sizeof(a));
+  a.sp = h->spec;
+  a.dv.n_nodes = nodes.n_nodes;
+  a.dv.node_t = nodes.node_t;
+  a.dv.t_start = h->grid[0];
+  if (with_data) {
+    a.dv.n_data = h->D;
+    a.dv.dat_y = h->d_y;
+    a.dv.dat_yerr = h->d_yerr;
+    a.dv.dat_dx = h->d_dx;
+    a.dv.dat_Dx = h->d_Dx;
+    a.dv.dat_lo = h->d_lo;
+    a.dat_orig = h->d_orig;
+  }
+  a.prior_enabled = use_prior ? h->prior.enabled : 0;
+  for (int i = 0; i < MP_MAX_NDIM; ++i) {
+    a.lower[i] = h->prior.lower[i];
+    a.upper[i] = h->prior.upper[i];
+  }
+  a.ndim = ndim;
+  a.W = W;
+  return MP_OK;
+}
+
+template <int MODE>
+static int launch_eval(const KernelArgs& a, cudaStream_t stream) {
+  if (a.W == 0) return MP_OK;
+  // small ensembles: 32-thread blocks spread the warps over more SMs
+  if (a.W <= 148 * 64 * 4) {
+    eval_kernel<MODE, 32><<<(a.W + 31) / 32, 32, 0, stream>>>(a);
+  } else {
+    eval_kernel<MODE, 64><<<(a.W + 63) / 64, 64, 0, stream>>>(a);
+  }
+  MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
+extern "C" int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32_t W, int32_t ndim,
+                                      double* d_lnp, int32_t* d_status, int32_t* d_n_rhs, void* stream) {
+  if (!h || (W > 0 && (!d_theta || !d_lnp))) return fail(MP_ERR_BAD_ARG, "mp_lnprob_batch_device: null pointer");
+  MP_CUDA(cudaSetDevice(h->device));
+  KernelArgs a;
+  int rc = fill_args(h, a, h->data_nodes, true, ndim, W, true);
+  if (rc) return rc;
+  a.theta = d_theta;
+  a.lnp = d_lnp;
+  a.status = d_status;
+  a.n_rhs = d_n_rhs;
+  return launch_eval<kModeLnprob>(a, (cudaStream_t)stream);
+}
+
+extern "C" int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int32_t ndim, double* lnp,
+                               int32_t* status, int32_t* n_rhs) {
+  if (!h || (W > 0 && (!theta || !lnp))) return fail(MP_ERR_BAD_ARG, "mp_lnprob_batch: null pointer");
+  if (ndim < 6 || ndim > MP_MAX_NDIM) return fail(MP_ERR_BAD_ARG, "ndim must be 6, 7, 8 or 9");
+  if (W == 0) return MP_OK;
+  MP_CUDA(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = ensure(&h->s_theta, &h->cap_theta, (size_t)W * MP_MAX_NDIM))) return rc;
+  if (W > (int)h->cap_w) {
+    cudaFree(h->s_lnp); cudaFree(h->s_status); cudaFree(h->s_nrhs);
+    h->s_lnp = nullptr; h->s_status = nullptr; h->s_nrhs = nullptr; h->cap_w = 0;
+    MP_CUDA(cudaMalloc((void**)&h->s_lnp, (size_t)W * sizeof(double)));
+    MP_CUDA(cudaMalloc((void**)&h->s_status, (size_t)W * sizeof(int)));
+    MP_CUDA(cudaMalloc((void**)&h->s_nrhs, (size_t)W * sizeof(int)));
+    h->cap_w = W;
+  }
+  MP_CUDA(cudaMemcpyAsync(h->s_theta, theta, (size_t)W * ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  rc = mp_lnprob_batch_device(h, h->s_theta, W, ndim, h->s_lnp, h->s_status, h->s_nrhs, h->stream);
+  if (rc) return rc;
+  MP_CUDA(cudaMemcpyAsync(lnp, h->s_lnp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (status) MP_CUDA(cudaMemcpyAsync(status, h->s_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (n_rhs) MP_CUDA(cudaMemcpyAsync(n_rhs, h->s_nrhs, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MP_CUDA(cudaStreamSynchronize(h->stream));
+  return MP_OK;
+}
+
+extern "C" int mp_model_at_data(mp_handle* h, const double* pars, int32_t W, int32_t ndim, double* out,
+                                int32_t* status) {
+  if (!h || (W > 0 && (!pars || !out))) return fail(MP_ERR_BAD_ARG, "mp_model_at_data: null pointer");
+  if (h->D == 0) return fail(MP_ERR_NO_DATA, "mp_model_at_data: handle has no data times");
+  if (W == 0) return MP_OK;
+  MP_CUDA(cudaSetDevice(h->device));
+  KernelArgs a;
+  int rc = fill_args(h, a, h->data_nodes, true, ndim, W, false);
+  if (rc) return rc;
+  a.sp.unlog_mask = 0;  // model_lum takes physical parameters
+  if ((rc = ensure(&h->s_theta, &h->cap_theta, (size_t)W * MP_MAX_NDIM))) return rc;
+  if ((rc = ensure(&h->s_out, &h->cap_out, (size_t)W * h->D))) return rc;
+  size_t capw = h->cap_w;
+  if (W > (int)capw) {
+    cudaFree(h->s_status);
+    h->s_status = nullptr;
+    cudaFree(h->s_lnp); cudaFree(h->s_nrhs);
+    h->s_lnp = nullptr; h->s_nrhs = nullptr; h->cap_w = 0;
+    MP_CUDA(cudaMalloc((void**)&h->s_lnp, (size_t)W * sizeof(double)));
+    MP_CUDA(cudaMalloc((void**)&h->s_status, (size_t)W * sizeof(int)));
+    MP_CUDA(cudaMalloc((void**)&h->s_nrhs, (size_t)W * sizeof(int)));
+    h->cap_w = W;
+  }
+  MP_CUDA(cudaMemcpyAsync(h->s_theta, pars, (size_t)W * ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  a.theta = h->s_theta;
+  a.out = h->s_out;
+  a.status = h->s_status;
+  if ((rc = launch_eval<kModeModelAtData>(a, h->stream))) return rc;
+  MP_CUDA(cudaMemcpyAsync(out, h->s_out, (size_t)W * h->D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (status) MP_CUDA(cudaMemcpyAsync(status, h->s_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  MP_CUDA(cudaStreamSynchronize(h->stream));
+  return MP_OK;
+}
+
+static int curve_node_set(mp_handle* h, int stride, DeviceNodes** out) {
+  if (stride < 1) stride = 1;
+  auto it = h->curve_nodes.find(stride);
+  if (it == h->curve_nodes.end()) {
+    std::vector<double> nt;
+    std::vector<int> gi;
+    build_curve_nodes(h->grid.data(), (int)h->grid.size(), stride, nt, gi);
+    DeviceNodes dn;
+    dn.n_nodes = (int)nt.size();
+    int rc = upload(&dn.node_t, nt);
+    if (rc) return rc;
+    it = h->curve_nodes.emplace(stride, dn).first;
+  }
+  *out = &it->second;
+  return MP_OK;
+}
+
+extern "C" int32_t mp_curve_nodes(const mp_handle* h, int32_t node_stride) {
+  if (!h) return 0;
+  if (node_stride < 1) node_stride = 1;
+  const int G = (int)h->grid.size();
+  int n = (G + node_stride - 1) / node_stride;
+  if ((n - 1) * node_stride != G - 1) ++n;
+  return n;
+}
+
+extern "C" int mp_model_curves_device(mp_handle* h, const double* d_pars, int32_t W, int32_t ndim,
+                                      int32_t node_stride, double* d_out, double* d_state,
+                                      int32_t* d_status, void* stream) {
+  if (!h || (W > 0 && (!d_pars || !d_out))) return fail(MP_ERR_BAD_ARG, "mp_model_curves_device: null pointer");
+  MP_CUDA(cudaSetDevice(h->device));
+  DeviceNodes* dn = nullptr;
+  int rc = curve_node_set(h, node_stride, &dn);
+  if (rc) return rc;
+  KernelArgs a;
+  if ((rc = fill_args(h, a, *dn, false, ndim, W, false))) return rc;
+  a.sp.unlog_mask = 0;
+  a.theta = d_pars;
+  a.out = d_out;
+  a.state = d_state;
+  a.status = d_status;
+  return launch_eval<kModeCurves>(a, (cudaStream_t)stream);
+}
+
+extern "C" int mp_model_curves(mp_handle* h, const double* pars, int32_t W, int32_t ndim, int32_t node_stride,
+                               double* out, double* state, int32_t* status) {
+  if (!h || (W > 0 && (!pars || !out))) return fail(MP_ERR_BAD_ARG, "mp_model_curves: null pointer");
+  if (ndim < 6 || ndim > MP_MAX_NDIM) return fail(MP_ERR_BAD_ARG, "ndim must be 6, 7, 8 or 9");
+  if (W == 0) return MP_OK;
+  MP_CUDA(cudaSetDevice(h->device));
+  const size_t Gs = (size_t)mp_curve_nodes(h, node_stride);
+  int rc;
+  if ((rc = ensure(&h->s_theta, &h->cap_theta, (size_t)W * MP_MAX_NDIM))) return rc;
+  if ((rc = ensure(&h->s_out, &h->cap_out, (size_t)W * 3 * Gs))) return rc;
+  if (state && (rc = ensure(&h->s_state, &h->cap_state, (size_t)W * 2 * Gs))) return rc;
+  int* d_status = nullptr;
+  if (status) MP_CUDA(cudaMalloc((void**)&d_status, (size_t)W * sizeof(int)));
+  MP_CUDA(cudaMemcpyAsync(h->s_theta, pars, (size_t)W * ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  rc = mp_model_curves_device(h, h->s_theta, W, ndim, node_stride, h->s_out, state ? h->s_state : nullptr,
+                              d_status, h->stream);
+  if (!rc) {
+    cudaMemcpyAsync(out, h->s_out, (size_t)W * 3 * Gs * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (state) cudaMemcpyAsync(state, h->s_state, (size_t)W * 2 * Gs * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (status) cudaMemcpyAsync(status, d_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) rc = fail(MP_ERR_CUDA, std::string("mp_model_curves: ") + cudaGetErrorString(e));
+  }
+  if (d_status) cudaFree(d_status);
+  return rc;
+}
+
+extern "C" int mp_rhs_batch(const mp_model_spec* spec, const double* y, const double* t, const double* pars,
+                            const double* knobs, int32_t W, double* dydt, int32_t device) {
+  if (!spec || !y || !t || !pars || !knobs || !dydt || W < 0) return fail(MP_ERR_BAD_ARG, "mp_rhs_batch: null pointer");
+  if (W == 0) return MP_OK;
+  if (mp_device_count() <= device || device < 0)
+    return fail(MP_ERR_CUDA, "mp_rhs_batch: no such CUDA device (magprop_b200 has no CPU path)");
+  MP_CUDA(cudaSetDevice(device));
+  double *d_y = nullptr, *d_t = nullptr, *d_p = nullptr, *d_o = nullptr;
+  MP_CUDA(cudaMalloc((void**)&d_y, (size_t)W * 2 * sizeof(double)));
+  MP_CUDA(cudaMalloc((void**)&d_t, (size_t)W * sizeof(double)));
+  MP_CUDA(cudaMalloc((void**)&d_p, (size_t)W * 5 * sizeof(double)));
+  MP_CUDA(cudaMalloc((void**)&d_o, (size_t)W * 2 * sizeof(double)));
+  MP_CUDA(cudaMemcpy(d_y, y, (size_t)W * 2 * sizeof(double), cudaMemcpyHostToDevice));
+  MP_CUDA(cudaMemcpy(d_t, t, (size_t)W * sizeof(double), cudaMemcpyHostToDevice));
+  MP_CUDA(cudaMemcpy(d_p, pars, (size_t)W * 5 * sizeof(double), cudaMemcpyHostToDevice));
+  rhs_kernel<<<(W + 127) / 128, 128>>>(spec->inertia_factor, spec->mdot_factor, spec->breakup_rhs, d_y, d_t, d_p,
+                                       knobs[0], knobs[1], knobs[2], knobs[3], W, d_o);
+  MP_CUDA(cudaGetLastError());
+  MP_CUDA(cudaMemcpy(dydt, d_o, (size_t)W * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+  cudaFree(d_y); cudaFree(d_t); cudaFree(d_p); cudaFree(d_o);
+  return MP_OK;
+}
+
+extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_lnp, int32_t nwalkers,
+                                    int32_t ndim, const int32_t* d_active, int32_t n_active,
+                                    const int32_t* d_complement, int32_t n_complement, double a,
+                                    uint64_t seed, uint64_t step, int32_t* d_accepted, int32_t* d_n_rhs,
+                                    void* stream) {
+  if (!h || !d_coords || !d_lnp || !d_active || !d_complement || n_active < 0 || n_complement <= 0 ||
+      nwalkers <= 0)
+    return fail(MP_ERR_BAD_ARG, "mp_stretch_half_step: null pointer or empty set");
+  MP_CUDA(cudaSetDevice(h->device));
+  StretchArgs s;
+  int rc = fill_args(h, s.k, h->data_nodes, true, ndim, n_active, true);
+  if (rc) return rc;
+  s.k.n_rhs = d_n_rhs;
+  s.coords = d_coords;
+  s.lnp = d_lnp;
+  s.active = d_active;
+  s.complement = d_complement;
+  s.n_active = n_active;
+  s.n_complement = n_complement;
+  s.a = a;
+  s.seed = seed;
+  s.step = step;
+  s.accepted = d_accepted;
+  if (n_active == 0) return MP_OK;
+  if (n_active <= 148 * 64 * 4) stretch_kernel<32><<<(n_active + 31) / 32, 32, 0, (cudaStream_t)stream>>>(s);
+  else stretch_kernel<64><<<(n_active + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s);
+  MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
+extern "C" int mp_fp64_peak_tflops(int32_t device, double* tflops) {
+  if (!tflops) return fail(MP_ERR_BAD_ARG, "mp_fp64_peak_tflops: null pointer");
+  if (mp_device_count() <= device || device < 0) return fail(MP_ERR_CUDA, "no such CUDA device");
+  MP_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MP_CUDA(cudaGetDeviceProperties(&prop, device));
+  double* d = nullptr;
+  MP_CUDA(cudaMalloc((void**)&d, 8));
+  const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+  cudaEvent_t e0, e1;
+  MP_CUDA(cudaEventCreate(&e0));
+  MP_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    MP_CUDA(cudaEventRecord(e0));
+    dfma_peak_kernel<<<blocks, 256>>>(d, iters, 1.0 + rep);
+    MP_CUDA(cudaEventRecord(e1));
+    MP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    MP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return MP_OK;
+}

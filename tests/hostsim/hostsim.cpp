@@ -1,0 +1,89 @@
+// hostsim.cpp -- TEST INFRASTRUCTURE.  Compiles magprop_core.cuh for the host
+// (g++, no CUDA) so the per-walker algorithm can be debugged against the oracle
+// in the GPU-less build container.  Never linked into or loaded by the package;
+// the product path is the CUDA library only.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../magprop_b200/csrc/magprop_host.hpp"
+
+using namespace mp;
+
+static DataView view_of(const NodeProgram& np, double t_start) {
+  DataView dv;
+  dv.n_nodes = (int)np.node_t.size();
+  dv.n_data = (int)np.y.size();
+  dv.node_t = np.node_t.data();
+  dv.dat_y = np.y.data();
+  dv.dat_yerr = np.yerr.data();
+  dv.dat_dx = np.dx.data();
+  dv.dat_Dx = np.Dx.data();
+  dv.dat_lo = np.lo.data();
+  dv.t_start = t_start;
+  return dv;
+}
+
+extern "C" int hs_lnprob(const mp_model_spec* ms, const mp_prior_spec* pr, const double* grid, int G,
+                         const double* t, const double* y, const double* yerr, int D,
+                         const double* theta, int W, int ndim, double* lnp, int* status, int* nrhs,
+                         int* nsteps) {
+  NodeProgram np;
+  int rc = build_node_program(grid, G, t, y, yerr, D, np);
+  if (rc) return rc;
+  Spec sp = make_spec(*ms);
+  DataView dv = view_of(np, grid[0]);
+  std::vector<double> buf(64);
+  for (int w = 0; w < W; ++w) {
+    const double* th = theta + (size_t)w * ndim;
+    int st = 0, nr = 0;
+    double out = -INFINITY;
+    if (pr->enabled && !prior_accepts(th, ndim, pr->lower, pr->upper)) {
+      st = kWalkerPriorReject;
+    } else {
+      double pars[6], de, pe, fb;
+      unpack_theta(sp, th, ndim, pars, de, pe, fb);
+      Walker wk;
+      walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
+      double chi2 = evaluate_walker<kModeLnprob, 64>(sp, dv, wk, buf.data(), 1, st, nr, nullptr, nullptr, 1, nullptr);
+      double ll = -0.5 * chi2;
+      if (st & kWalkerIntegratorFail) ll = -INFINITY;
+      else if (!std::isfinite(ll)) { st |= kWalkerNonfiniteLnlike; ll = -INFINITY; }
+      out = ll;
+    }
+    lnp[w] = out;
+    if (status) status[w] = st;
+    if (nrhs) nrhs[w] = nr;
+  }
+  (void)nsteps;
+  return 0;
+}
+
+extern "C" int hs_curves(const mp_model_spec* ms, const double* grid, int G, const double* pars_in,
+                         int W, int ndim, int stride, double* out, double* state, int* status,
+                         int* nrhs) {
+  std::vector<double> node_t;
+  std::vector<int> gi;
+  build_curve_nodes(grid, G, stride, node_t, gi);
+  NodeProgram np;
+  np.node_t = node_t;
+  Spec sp = make_spec(*ms);
+  sp.unlog_mask = 0;
+  DataView dv = view_of(np, grid[0]);
+  const int Gs = (int)node_t.size();
+  std::vector<double> buf(64);
+  for (int w = 0; w < W; ++w) {
+    double pars[6], de, pe, fb;
+    unpack_theta(sp, pars_in + (size_t)w * ndim, ndim, pars, de, pe, fb);
+    Walker wk;
+    walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
+    int st = 0, nr = 0;
+    evaluate_walker<kModeCurves, 64>(sp, dv, wk, buf.data(), 1, st, nr, out + (size_t)w * 3 * Gs,
+                                     state ? state + (size_t)w * 2 * Gs : nullptr, 1, nullptr);
+    if (status) status[w] = st;
+    if (nrhs) nrhs[w] = nr;
+  }
+  return Gs;
+}
+
+extern "C" double hs_disc_S(double u) { return disc_S(u); }
