@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- walker-lnprob evaluations/s of the magprop likelihood hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): the Classic, Sloped and Stuttering
+synthetic datasets (recipe of generate_data.py:47-71, seed 20170613, 50 points)
+and 256-walker ensembles started as synth_mcmc.py:175-176 does (log-space truth
++ 1e-4*randn).  One *step* evaluates lnprob once for every walker of E
+independent 256-walker ensembles on each of the three datasets (3 launches);
+E = --ensembles per GPU (weak scaling: each rank owns its own ensembles, no
+data-path collective -- independent chains need none).
+
+Printed JSON (one line, rank 0): the contract of the task statement, plus
+  roofline      FP64 FMA roofline of eval_kernel (peak measured live by a DFMA
+                micro-benchmark on the same GPU; MEASURED_PEAKS.json has no FP64 entry)
+  cpu_baseline  the oracle (CPU port of the reference's odeint path) timed on
+                this box's host cores on a bounded sample of the same workload
+  e2e           the same metric through the C-ABI host-pointer call
+                (mp_lnprob_batch: H2D of theta, launch, D2H of lnprob, every step)
+  extra         latency-bound exact config-2 shape (256 walkers), posterior-spread
+                and prior-uniform ensembles, fused stretch-move MCMC steps/s
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+DATASETS = ("Classic", "Sloped", "Stuttering")
+METRIC = "walker_lnprob_evals_per_sec"
+UNIT = "evals/s"
+F_RHS, F_LUM, F_CHI = 440.0, 400.0, 12.0      # algorithmic FP64 flop per unit
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ensembles", type=int, default=1024, help="independent 256-walker ensembles per dataset per GPU")
+    ap.add_argument("--nwalk", type=int, default=256)
+    ap.add_argument("--cpu-evals", type=int, default=0, help="CPU-baseline sample size (0: ~16 per core)")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def load_datasets():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "lnprob_script.npz"))
+    return {n: (g[f"{n}_x"], g[f"{n}_y"], g[f"{n}_yerr"]) for n in ("Humped",) + DATASETS}
+
+
+def workload_config(args):
+    return {
+        "workload": "configs[1]: Classic+Sloped+Stuttering synthetic datasets (50 pts, 25% errors, seed 20170613); "
+                    f"{args.ensembles} independent {args.nwalk}-walker ensembles per dataset per GPU, walkers = "
+                    "log-truth + 1e-4*randn (synth_mcmc.py:175-176); one step = lnprob of every walker on every dataset",
+        "datasets": list(DATASETS), "nwalk": args.nwalk, "ensembles_per_gpu": args.ensembles,
+        "walkers_per_step_per_gpu": args.ensembles * args.nwalk * len(DATASETS),
+        "model": "script variant (code/synthetic_datasets/funcs.py), 6 parameters",
+        "l2": "flushed between timed steps (256 MiB write)",
+    }
+
+
+# ------------------------------------------------------------------------------------ CPU legs
+def _cpu_task(a):
+    from oracle import magprop_oracle as O
+    theta, x, y, yerr = a
+    return O.lnprob(theta, x, y, yerr, O.script_spec(), O.SCRIPT_LOWER, O.SCRIPT_UPPER)
+
+
+def cpu_throughput(n_evals, seed=0, procs=None):
+    """Oracle lnprob (the reference's odeint path, restated) over a Pool, as the
+    reference's own Pool.map does (synth_mcmc.py:178-185)."""
+    from multiprocessing import get_context
+    from oracle import magprop_oracle as O
+    data = load_datasets()
+    rng = np.random.RandomState(1234 + seed)
+    procs = procs or os.cpu_count() or 1
+    tasks = []
+    for i in range(n_evals):
+        name = DATASETS[i % len(DATASETS)]
+        tasks.append((O.SYNTH_TRUTHS_LOG[name] + 1e-4 * rng.randn(6), *data[name]))
+    with get_context("fork").Pool(procs) as pool:
+        pool.map(_cpu_task, tasks[:procs])          # warm the workers (imports)
+        t0 = time.perf_counter()
+        pool.map(_cpu_task, tasks, chunksize=1)
+        dt = time.perf_counter() - t0
+    return n_evals / dt, dt, procs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 2 * cores)
+    import scipy
+    vals = []
+    for s in range(args.warmup + args.steps):
+        v, dt, procs = cpu_throughput(per_step, seed=s)
+        if s >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.sum([per_step for _ in vals]) / np.sum([dt for _, dt in vals]))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean([dt for _, dt in vals]) * 1e3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload_config(args), sample=f"{per_step} walkers per step across {cores} processes"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} lnprob evaluations per step, {args.steps} steps, "
+                                   f"multiprocessing.Pool({cores}); oracle = scipy {scipy.__version__} odeint (LSODA) "
+                                   "restatement of the reference path"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU leg
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=5)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from magprop_b200 import _capi as A
+    from magprop_b200.engine import Likelihood, time_grid, fp64_peak_tflops
+    from oracle import magprop_oracle as O   # truths / prior constants only (no compute)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    data = load_datasets()
+    grid = time_grid(None)
+    spec = A.script_model_spec()
+    liks = {n: Likelihood(spec, grid, *data[n], O.SCRIPT_LOWER, O.SCRIPT_UPPER, device=local) for n in DATASETS}
+    W = args.ensembles * args.nwalk
+    rng = np.random.RandomState(20170613 + rank)
+    host_theta, d_theta, d_lnp, d_nrhs = {}, {}, {}, {}
+    for n in DATASETS:
+        th = O.SYNTH_TRUTHS_LOG[n] + 1e-4 * rng.randn(W, 6)
+        host_theta[n] = torch.from_numpy(th).pin_memory()
+        d_theta[n] = host_theta[n].to(dev)
+        d_lnp[n] = torch.empty(W, dtype=torch.float64, device=dev)
+        d_nrhs[n] = torch.empty(W, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        for n in DATASETS:
+            liks[n].lnprob_device(d_theta[n].data_ptr(), W, 6, d_lnp[n].data_ptr(), 0, d_nrhs[n].data_ptr(), stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peak = fp64_peak_tflops(local)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xFF)                       # L2 flush, outside the event pair
+        ev[s][0].record()
+        step()
+        ev[s][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    evals_per_step = W * len(DATASETS) * world
+    value = evals_per_step * args.steps / (ms_total * 1e-3)
+
+    # all walkers finite?
+    bad = sum(int((~torch.isfinite(d_lnp[n])).sum().item()) for n in DATASETS)
+    mean_nrhs = float(np.mean([d_nrhs[n].double().mean().item() for n in DATASETS]))
+    D = 50
+    n_lum = float(np.mean([len(np.unique(data[n][0])) for n in DATASETS]))
+    flop_per_eval = mean_nrhs * F_RHS + n_lum * F_LUM + D * F_CHI
+    achieved = (value / world) * flop_per_eval / 1e12
+
+    # ---- e2e through the host-pointer C-ABI call -------------------------------------
+    np_theta = {n: host_theta[n].numpy() for n in DATASETS}
+    out_h = {n: np.empty(W) for n in DATASETS}
+
+    def e2e_step():
+        for n in DATASETS:
+            A.check(liks[n]._lib.mp_lnprob_batch(liks[n]._h, A.ptr(np_theta[n]), W, 6, A.ptr(out_h[n]), None, None))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = evals_per_step * args.steps / float(e2e_dt.item())
+
+    extra = {}
+    if not args.no_extra:
+        extra = extras(args, liks, data, dev, rank, world, torch, O, A)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        n_cpu = args.cpu_evals or 16 * (os.cpu_count() or 1)
+        v, dt, procs = cpu_throughput(n_cpu)
+        import scipy
+        cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+               "sample": f"{n_cpu} lnprob evaluations of the same walker draws in {dt:.1f} s, multiprocessing.Pool({procs}); "
+                         f"oracle = scipy {scipy.__version__} odeint restatement of the reference path"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "kernel": "mp::eval_kernel<kModeLnprob>",
+                         "algorithmic_flop_per_eval": flop_per_eval, "mean_rhs_per_eval": mean_nrhs,
+                         "peak_source": "live DFMA micro-benchmark (mp_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
+                         "hbm_bytes_per_eval": 48 + 8 + 4},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * 6 * 8 * len(DATASETS),
+                    "d2h_bytes_per_step": W * 8 * len(DATASETS)},
+            "gpu_launches": args.steps * len(DATASETS),
+            "clocks": clocks,
+            "nonfinite_lnprob": bad,
+            "wall_s_timed_region": wall,
+            "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    for lk in liks.values():
+        lk.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extras(args, liks, data, dev, rank, world, torch, O, A):
+    """Secondary measurements (not the headline): other ensemble shapes."""
+    out = {}
+    rng = np.random.RandomState(99 + rank)
+    lk = liks["Classic"]
+    name = "Classic"
+
+    def timed(theta, reps=5):
+        W = theta.shape[0]
+        d_t = torch.from_numpy(np.ascontiguousarray(theta)).to(dev)
+        d_l = torch.empty(W, dtype=torch.float64, device=dev)
+        d_n = torch.empty(W, dtype=torch.int32, device=dev)
+        for _ in range(2):
+            lk.lnprob_device(d_t.data_ptr(), W, 6, d_l.data_ptr(), 0, d_n.data_ptr())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            lk.lnprob_device(d_t.data_ptr(), W, 6, d_l.data_ptr(), 0, d_n.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        return {"walkers": W, "ms": ms, "evals_per_s": W / ms * 1e3, "mean_rhs": float(d_n.double().mean().item()),
+                "max_rhs": int(d_n.max().item())}
+
+    truth = O.SYNTH_TRUTHS_LOG[name]
+    out["config2_exact_half_step_128_walkers"] = timed(truth + 1e-4 * rng.randn(128, 6), reps=20)
+    for W in (10 ** 2, 10 ** 4, 10 ** 6):
+        out[f"ball_1e-4_W{W}"] = timed(truth + 1e-4 * rng.randn(W, 6))
+    out["posterior_spread_0.05_W262144"] = timed(np.clip(truth + 0.05 * rng.randn(1 << 18, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER))
+    out["prior_uniform_W65536"] = timed(rng.uniform(O.SCRIPT_LOWER, O.SCRIPT_UPPER, size=(1 << 16, 6)), reps=1)
+    return out
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

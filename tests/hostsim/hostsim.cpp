@@ -87,3 +87,39 @@ extern "C" int hs_curves(const mp_model_spec* ms, const double* grid, int G, con
 }
 
 extern "C" double hs_disc_S(double u) { return disc_S(u); }
+
+// node program of a dataset, for tests of the host-side preparation
+extern "C" int hs_node_program(const double* grid, int G, const double* t, const double* y, const double* yerr,
+                               int D, int* n_nodes, int* node_grid_index, int* lo, double* dx, double* Dx,
+                               int* order) {
+  NodeProgram np;
+  int rc = build_node_program(grid, G, t, y, yerr, D, np);
+  if (rc) return rc;
+  *n_nodes = (int)np.node_t.size();
+  for (size_t i = 0; i < np.node_t.size(); ++i) node_grid_index[i] = np.node_grid_index[i];
+  for (int i = 0; i < D; ++i) { lo[i] = np.lo[i]; dx[i] = np.dx[i]; Dx[i] = np.Dx[i]; order[i] = np.order[i]; }
+  return 0;
+}
+
+extern "C" int hs_model_at(const mp_model_spec* ms, const double* grid, int G, const double* t, int D,
+                           const double* pars_in, int W, int ndim, double* out, int* status) {
+  std::vector<double> ones(D, 1.0);
+  NodeProgram np;
+  int rc = build_node_program(grid, G, t, ones.data(), ones.data(), D, np);
+  if (rc) return rc;
+  Spec sp = make_spec(*ms);
+  sp.unlog_mask = 0;
+  DataView dv = view_of(np, grid[0]);
+  std::vector<double> buf(64);
+  for (int w = 0; w < W; ++w) {
+    double pars[6], de, pe, fb;
+    unpack_theta(sp, pars_in + (size_t)w * ndim, ndim, pars, de, pe, fb);
+    Walker wk;
+    walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
+    int st = 0, nr = 0;
+    evaluate_walker<kModeModelAtData, 64>(sp, dv, wk, buf.data(), 1, st, nr, out + (size_t)w * D, nullptr, 1,
+                                          np.order.data());
+    if (status) status[w] = st;
+  }
+  return 0;
+}
