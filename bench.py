@@ -138,6 +138,22 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self._stop_evt = index, [], threading.Event()
 
     def run(self):
+        try:                                    # NVML: ~1 ms per sample
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.index)
+            names = {"hw_slowdown": N.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": N.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": N.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": N.nvmlClocksEventReasonSwPowerCap}
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            while not self._stop_evt.is_set():
+                sm = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+                mask = N.nvmlDeviceGetCurrentClocksEventReasons(h)
+                pw = N.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append([str(sm), str(mx), str(pw)] + [("Active" if mask & v else "Not Active") for v in names.values()])
+                self._stop_evt.wait(0.01)
+            return
+        except Exception:
+            pass
         while not self._stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",

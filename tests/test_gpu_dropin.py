@@ -27,7 +27,7 @@ def test_model_light_curve(built, golden):
     t, Ltot, Lprop, Ldip = model_lc([1.0, 5.0, 0.001, 100.0, 0.1, 1.0])
     assert np.isclose(t, f["lc_t"]).all() and np.isclose(Ltot, f["lc_Ltot"]).all()
     assert np.isclose(Lprop, f["lc_Lprop"]).all() and np.isclose(Ldip, f["lc_Ldip"]).all()
-    assert (t == f["lc_t"]).all()
+    assert (t == np.logspace(0.0, 6.0, num=10001, base=10.0)).all()
     with pytest.raises(ValueError):
         model_lc([1.0, 5.0, 0.001, 100.0, 0.1, 1.0], GRBtype="X")       # magnetar/funcs.py:138-141
 
