@@ -83,6 +83,8 @@ _ip = C.POINTER(C.c_int32)
 
 
 def lib_path() -> str:
+    if os.environ.get("MAGPROP_B200_LIB"):      # developer override (A/B builds of the same CUDA library)
+        return os.environ["MAGPROP_B200_LIB"]
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmagprop_b200.so")
 
 

@@ -29,7 +29,9 @@
 #if defined(__CUDACC__)
 #define MP_HD __host__ __device__ __forceinline__
 #define MP_TABLE_QUALIFIER __device__ const
+#define MP_CONST_QUALIFIER __constant__ const
 #else
+#define MP_CONST_QUALIFIER static const
 #define MP_HD inline
 #define MP_TABLE_QUALIFIER static const
 #endif
@@ -107,42 +109,60 @@ MP_HD double bitsd(int64_t i) {
 #endif
 }
 
-MP_HD double disc_S(double u) {
+// Locate u in the table: row pointer and local coordinate s in [-1,1).
+struct TableAt {
+  const double* row;
+  double s;
+  int e;   // binade of u
+};
+
+MP_HD bool table_locate(double u, TableAt& ta) {
   const int64_t b = dbits(u);
   const int e = (int)((b >> 52) & 0x7ff) - 1023;
-  if (e >= MP_DISC_EMIN && e <= MP_DISC_EMAX) {   // also false for u<=0 / NaN patterns with odd exponents
-    const int sub = (int)((b >> (52 - MP_DISC_NSUB_LOG2)) & ((1 << MP_DISC_NSUB_LOG2) - 1));
-    const double* row = &mp_disc_table[((e - MP_DISC_EMIN) << MP_DISC_NSUB_LOG2) + sub][0];
-    // mantissa in [1,2) -> local coordinate s in [-1,1)
-    const double m = bitsd((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-    const double centre = 1.0 + (sub + 0.5) * (1.0 / (1 << MP_DISC_NSUB_LOG2));
-    const double s = (m - centre) * (double)(2 << MP_DISC_NSUB_LOG2);
-    // degree-10 polynomial, Estrin-style split into even/odd halves for ILP
-    const double s2 = s * s;
-    double ev = ldg(row + 10);
-    double od = ldg(row + 9);
-    ev = fma(ev, s2, ldg(row + 8));
-    od = fma(od, s2, ldg(row + 7));
-    ev = fma(ev, s2, ldg(row + 6));
-    od = fma(od, s2, ldg(row + 5));
-    ev = fma(ev, s2, ldg(row + 4));
-    od = fma(od, s2, ldg(row + 3));
-    ev = fma(ev, s2, ldg(row + 2));
-    od = fma(od, s2, ldg(row + 1));
-    ev = fma(ev, s2, ldg(row + 0));
-    return fma(od, s, ev);
-  }
-  if (!(u > 0.0)) return NAN;
-  if (e > MP_DISC_EMAX) {  // asymptotic series, u >= 2^22: next term 16/u^3 < 3e-19
+  ta.e = e;
+  if (b < 0 || e < MP_DISC_EMIN || e > MP_DISC_EMAX) return false;   // u <= 0, NaN/inf, out of range
+  const int sub = (int)((b >> (52 - MP_DISC_NSUB_LOG2)) & ((1 << MP_DISC_NSUB_LOG2) - 1));
+  ta.row = &mp_disc_table[((e - MP_DISC_EMIN) << MP_DISC_NSUB_LOG2) + sub][0];
+  // mantissa in [1,2) -> local coordinate
+  const double m = bitsd((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double centre = 1.0 + (sub + 0.5) * (1.0 / (1 << MP_DISC_NSUB_LOG2));
+  ta.s = (m - centre) * (double)(2 << MP_DISC_NSUB_LOG2);
+  return true;
+}
+
+// degree-10 polynomial, split into even/odd halves for ILP
+MP_HD double poly10(const double* c, double s) {
+  const double s2 = s * s;
+  double ev = ldg(c + 10);
+  double od = ldg(c + 9);
+  ev = fma(ev, s2, ldg(c + 8));
+  od = fma(od, s2, ldg(c + 7));
+  ev = fma(ev, s2, ldg(c + 6));
+  od = fma(od, s2, ldg(c + 5));
+  ev = fma(ev, s2, ldg(c + 4));
+  od = fma(od, s2, ldg(c + 3));
+  ev = fma(ev, s2, ldg(c + 2));
+  od = fma(od, s2, ldg(c + 1));
+  ev = fma(ev, s2, ldg(c + 0));
+  return fma(od, s, ev);
+}
+
+// S outside the table (rare): convergent series below 2^-10, asymptotic above 2^22.
+// Kept out of line so the hot stage loop stays small.
+#if defined(__CUDACC__)
+__device__ __host__ __noinline__
+#endif
+static double disc_S_outside(double u, int e) {
+  if (!(u > 0.0) || !(u < 1.0e300)) return NAN;
+  if (e > MP_DISC_EMAX) {  // next term 16/u^3 < 3e-19
     const double iu = 1.0 / u;
     const double c = cbrt(iu);
     const double p = iu * c * c;  // u^(-5/3)
     return p * fma(fma(40.0 / 9.0, iu, 5.0 / 3.0), iu, 1.0);
   }
-  // convergent series, u < 2^-10: e^-u u^(-2/3) sum u^k / (k! (k-2/3))
+  // e^-u u^(-2/3) sum_k u^k / (k! (k-2/3))
   const double c = cbrt(u);
-  double sum = 0.0, term = 1.0;
-  sum = -1.5;
+  double sum = -1.5, term = 1.0;
   for (int k = 1; k <= 6; ++k) {
     term *= u / k;
     sum += term / (k - 2.0 / 3.0);
@@ -150,15 +170,25 @@ MP_HD double disc_S(double u) {
   return exp(-u) * sum / (c * c);
 }
 
+MP_HD double disc_S(double u) {
+  TableAt ta;
+  if (table_locate(u, ta)) return poly10(ta.row, ta.s);
+  return disc_S_outside(u, ta.e);
+}
+
 // ---- per-walker constants ---------------------------------------------------
 struct Walker {
   // disc mass: M(t) = K*S(u) + C*exp(-(u-u0)), u = t*inv_tv + eps
   double inv_tv, eps, u0, K, C, M_init;
+  double u_late;   // for u >= u_late the transient C*exp(u0-u) is below 1e-18 of K*S(u): M = K*S(u)
+  double Kq;       // K^(-1/7): late-phase M^(-1/7) = Kq * Q(u)
   // right-hand side
   double A_rm;     // Rm(uncapped) = A_rm * M^(-2/7)
   double Cw;       // w(uncapped)  = Cw * M^(-3/7) * omega
   double Ccap;     // w(capped)    = Ccap / sqrt(omega)
   double kc;       // k*c : capped when Rm*omega >= k*c
+  double sGMA;     // sqrt(GM*A_rm): lever(uncapped) = sGMA * M^(-1/7)
+  double sGMkc;    // sqrt(GM*k*c):  lever(capped)   = sGMkc / sqrt(omega)
   double Cdip_I;   // mu^2/(6c^3)/I
   // luminosity stage (its own alpha/cs7/k/n may differ from the RHS's)
   double l_inv_tv, l_A_rm, l_Cw, l_Ccap, l_kc;
@@ -169,6 +199,21 @@ struct Walker {
 };
 
 MP_HD double pow_m17(double x) { return exp(log(x) * (-1.0 / 7.0)); }
+
+MP_HD double rcp_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  return __drcp_rn(x);
+#else
+  return 1.0 / x;
+#endif
+}
+MP_HD double rsqrt_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 
 // pars = physical (B, P, MdiscI, RdiscI, epsilon, delta)
 MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, double propeff,
@@ -187,6 +232,15 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
   const double ce = cbrt(epsilon);
   w.K = M0 * ce * ce;
   w.C = w.M_init - w.K * disc_S(w.u0);
+  // late phase: transient negligible (and u >= 1 so that S > 0 and Q is tabulated)
+  w.u_late = INFINITY;
+  w.Kq = 0.0;
+  if (w.K > 0.0) {
+    const double ua = fmax(w.u0 + 45.0, 1.0);
+    const double ratio = fabs(w.C) * exp(w.u0 - ua) / (w.K * disc_S(ua));
+    w.u_late = (ratio <= 1.0e-19) ? ua : ua + log(ratio * 1.0e19);
+    w.Kq = pow_m17(w.K);
+  }
   const double mu47 = exp(log(mu) * (4.0 / 7.0));
   const double gm17 = exp(log(kGM) * (-1.0 / 7.0));
   const double base = mu47 * gm17;
@@ -194,6 +248,8 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
   w.Cw = w.A_rm * sqrt(w.A_rm) / sqrt(kGM);
   w.kc = sp.rhs_k * kC;
   w.Ccap = w.kc * sqrt(w.kc) / sqrt(kGM);
+  w.sGMA = sqrt(kGM * w.A_rm);
+  w.sGMkc = sqrt(kGM * w.kc);
   w.Ldip_coef = (mu * mu) / (6.0 * (kC * kC * kC));
   w.Cdip_I = w.Ldip_coef * sp.inv_inertia;
   const double ltv = RdiscI * sp.lum_tv_per_R;
@@ -221,39 +277,63 @@ MP_HD double disc_mass(const Walker& w, double t) {
 // Quantities of the RHS that depend on time only (through the disc mass).
 struct DiscAt {
   double mdot;   // Mdisc/tvisc
-  double rm;     // uncapped Alfven radius
-  double wq;     // uncapped fastness / omega
+  double q;      // Mdisc^(-1/7)
+  double rm;     // uncapped Alfven radius  A_rm q^2
+  double wq;     // uncapped fastness / omega  Cw q^3
 };
 
 MP_HD DiscAt disc_at(const Walker& w, double t) {
-  const double M = disc_mass(w, t);
-  const double q = pow_m17(M);
+  const double u = fma(t, w.inv_tv, w.eps);
+  TableAt ta;
+  const bool in = table_locate(u, ta);
+  double M, q;
+  if (in && u >= w.u_late) {
+    // late phase: both S and Q = S^(-1/7) from the same table row -- no exp, no log
+    const double S = poly10(ta.row, ta.s);
+    const double Q = poly10(ta.row + MP_DISC_ROW, ta.s);
+    M = w.K * S;
+    q = w.Kq * Q;
+  } else {
+    const double S = in ? poly10(ta.row, ta.s) : disc_S_outside(u, ta.e);
+    const double E = exp(w.u0 - u);
+    M = fma(w.K, S, w.C * E);
+    q = pow_m17(M);
+  }
   const double q2 = q * q;
   DiscAt d;
   d.mdot = M * w.inv_tv;
+  d.q = q;
   d.rm = w.A_rm * q2;
   d.wq = w.Cw * q2 * q;
   return d;
 }
 
+// tanh to 2e-16 absolute (the torque needs absolute, not relative, accuracy).
+MP_HD double tanh_abs(double x) {
+  if (x > 19.1) return 1.0;
+  const double e2 = exp(2.0 * x);
+  return fma(-2.0, rcp_fast(e2 + 1.0), 1.0);
+}
+
 // d(omega)/dt: funcs.py:105-140 with the time-only factors hoisted into DiscAt.
 //   Rm/Rc = Rm * omega^(2/3) / GM^(1/3)  =>  w = (Rm/Rc)^(3/2) = Rm^(3/2) omega / sqrt(GM)
-//   capped (Rm >= k c/omega):            w = (k c)^(3/2) / sqrt(GM omega)
+//   capped (Rm >= k c/omega):  Rm = k c/omega,  w = (k c)^(3/2) / sqrt(GM omega)
+//   lever arm sqrt(GM Rm):     uncapped sqrt(GM A_rm) q ;  capped sqrt(GM k c) / sqrt(omega)
 //   Mdotacc - Mdotprop = (eta1 - eta2) Mdot = -tanh(n (w-1)) Mdot
 MP_HD double spin_rhs(const Spec& sp, const Walker& w, const DiscAt& d, double omega) {
-  double fast, rm;
+  double fast, lever;
   if (d.rm * omega >= w.kc) {
-    rm = w.kc / omega;
-    fast = w.Ccap / sqrt(omega);
+    const double r = rsqrt_fast(omega);
+    fast = w.Ccap * r;
+    lever = (w.kc >= kR * omega) ? w.sGMkc * r : sp.sqrt_GMR;
   } else {
-    rm = d.rm;
     fast = d.wq * omega;
+    lever = (d.rm >= kR) ? w.sGMA * d.q : sp.sqrt_GMR;
   }
   const double om2 = omega * omega;
   double nacc = 0.0;
   if (!(om2 > sp.omega2_breakup_rhs)) {
-    const double th = tanh(sp.rhs_n * (fast - 1.0));
-    const double lever = (rm >= kR) ? sqrt(kGM * rm) : sp.sqrt_GMR;
+    const double th = tanh_abs(sp.rhs_n * (fast - 1.0));
     nacc = -lever * d.mdot * th;
   }
   return fma(-w.Cdip_I * om2, omega, nacc * sp.inv_inertia);
@@ -300,15 +380,19 @@ MP_HD Lum luminosity(const Spec& sp, const Walker& w, double M, double omega) {
 }
 
 // ---- Dormand-Prince 5(4) with dense output --------------------------------
+// Coefficients: Dormand & Prince 1980; dense output: Hairer, Norsett & Wanner II.6.
+// Row s of kA gives stage s+1 from k1..ks; row 6 is the 5th-order weights (stage 7, FSAL).
+MP_CONST_QUALIFIER double kA[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+MP_CONST_QUALIFIER double kCn[7] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1, 1};
+
 struct Dopri {
-  // coefficients (Dormand & Prince 1980; dense output of Hairer, Norsett & Wanner II.6)
-  static constexpr double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
-  static constexpr double a21 = 1.0 / 5;
-  static constexpr double a31 = 3.0 / 40, a32 = 9.0 / 40;
-  static constexpr double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
-  static constexpr double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
-  static constexpr double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656;
-  static constexpr double a71 = 35.0 / 384, a73 = 500.0 / 1113, a74 = 125.0 / 192, a75 = -2187.0 / 6784, a76 = 11.0 / 84;
   static constexpr double e1 = 71.0 / 57600, e3 = -71.0 / 16695, e4 = 71.0 / 1920, e5 = -17253.0 / 339200, e6 = 22.0 / 525, e7 = -1.0 / 40;
   static constexpr double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0,
                           d4 = -10690763975.0 / 1880347072.0, d5 = 701980252875.0 / 199316789632.0,
@@ -318,7 +402,7 @@ struct Dopri {
 // State of the spin integration of one walker.
 struct Integrator {
   double t, omega, h, k1;        // k1 = f(t, omega) (FSAL)
-  double facold;
+  float facold;
   int rejected;                  // previous attempt was rejected
   // dense output of the last accepted step: omega(t0 + theta*hs)
   double t0, hs, r1, r2, r3, r4, r5, t1;
@@ -331,18 +415,27 @@ MP_HD double dense_eval(const Integrator& in, double tq) {
   return fma(th, fma(th1, fma(th, fma(th1, in.r5, in.r4), in.r3), in.r2), in.r1);
 }
 
+// f(t, omega) out of line: used by the (cold) initialisation only, so the hot
+// step loop below holds the single inlined copy of disc_at + spin_rhs.
+#if defined(__CUDACC__)
+__device__ __host__ __noinline__
+#endif
+static double spin_f_cold(const Spec& sp, const Walker& w, double t, double omega) {
+  const DiscAt d = disc_at(w, t);
+  return spin_rhs(sp, w, d, omega);
+}
+
 MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, double t_end,
                            Integrator& in) {
   in.t = t_start;
   in.omega = w.omega0;
-  in.facold = 1.0e-4;
+  in.facold = 1.0e-4f;
   in.rejected = 0;
   in.n_steps = 0;
   in.status = kWalkerOk;
   in.t0 = t_start; in.t1 = t_start; in.hs = 1.0;
   in.r1 = w.omega0; in.r2 = in.r3 = in.r4 = in.r5 = 0.0;
-  const DiscAt d0 = disc_at(w, t_start);
-  in.k1 = spin_rhs(sp, w, d0, in.omega);
+  in.k1 = spin_f_cold(sp, w, t_start, in.omega);
   // initial step (Hairer's hinit, order 5)
   const double sk = sp.rtol * fabs(in.omega);
   const double dnf = fabs(in.k1) / sk, dny = fabs(in.omega) / sk;
@@ -350,8 +443,7 @@ MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, doub
   const double span = t_end - t_start;
   h = fmin(h, span);
   const double y1 = fma(h, in.k1, in.omega);
-  const DiscAt d1 = disc_at(w, t_start + h);
-  const double f1 = spin_rhs(sp, w, d1, y1);
+  const double f1 = spin_f_cold(sp, w, t_start + h, y1);
   const double der2 = fabs(f1 - in.k1) / sk / h;
   const double der12 = fmax(der2, dnf);
   const double h1 = (der12 <= 1e-15) ? fmax(1.0e-6, fabs(h) * 1.0e-3)
@@ -359,6 +451,22 @@ MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, doub
   in.h = fmin(fmin(100.0 * h, h1), span);
   in.n_rhs = 2;
   if (!(isfinite(in.k1) && isfinite(in.h) && in.h > 0.0)) in.status = kWalkerIntegratorFail;
+}
+
+// Step-size factors of the PI controller (Hairer's dopri5: beta = 0.04, safety 0.9).
+// They steer the step size only, so single precision is ample:
+//   fac11 = err^(0.2 - 0.75 beta),  fac = fac11 / facold^beta
+MP_HD void controller(float err, float facold, float& fac11, float& fac) {
+  const float beta = 0.04f, expo1 = 0.2f - beta * 0.75f;
+#if defined(__CUDA_ARCH__)
+  const float l = __log2f(fmaxf(err, 1.0e-30f));
+  fac11 = exp2f(expo1 * l);
+  fac = exp2f(expo1 * l - beta * __log2f(facold));
+#else
+  const float l = log2f(fmaxf(err, 1.0e-30f));
+  fac11 = exp2f(expo1 * l);
+  fac = exp2f(expo1 * l - beta * log2f(facold));
+#endif
 }
 
 // Attempt one step; on acceptance advances (t, omega) and refreshes the dense
@@ -369,33 +477,37 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   double h = in.h;
   bool last = false;
   if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
-  const double k1 = in.k1;
-  const DiscAt m2 = disc_at(w, fma(D::c2, h, t));
-  const double k2 = spin_rhs(sp, w, m2, fma(h, D::a21 * k1, y));
-  const DiscAt m3 = disc_at(w, fma(D::c3, h, t));
-  const double k3 = spin_rhs(sp, w, m3, fma(h, fma(D::a32, k2, D::a31 * k1), y));
-  const DiscAt m4 = disc_at(w, fma(D::c4, h, t));
-  const double k4 = spin_rhs(sp, w, m4, fma(h, fma(D::a43, k3, fma(D::a42, k2, D::a41 * k1)), y));
-  const DiscAt m5 = disc_at(w, fma(D::c5, h, t));
-  const double k5 = spin_rhs(sp, w, m5, fma(h, fma(D::a54, k4, fma(D::a53, k3, fma(D::a52, k2, D::a51 * k1))), y));
   const double tn = last ? t_end : t + h;
-  const DiscAt m6 = disc_at(w, tn);
-  const double k6 = spin_rhs(sp, w, m6, fma(h, fma(D::a65, k5, fma(D::a64, k4, fma(D::a63, k3, fma(D::a62, k2, D::a61 * k1)))), y));
-  const double ynew = fma(h, fma(D::a76, k6, fma(D::a75, k5, fma(D::a74, k4, fma(D::a73, k3, D::a71 * k1)))), y);
-  const double k7 = spin_rhs(sp, w, m6, ynew);
+  double k[7];
+  k[0] = in.k1;
+  DiscAt m;
+  double ynew = y;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (int s = 1; s <= 6; ++s) {
+    double acc = kA[s][0] * k[0];
+    for (int j = 1; j < s; ++j) acc = fma(kA[s][j], k[j], acc);
+    const double ys = fma(h, acc, y);
+    if (s <= 5) m = disc_at(w, (s == 5) ? tn : fma(kCn[s], h, t));   // stage 7 reuses t_n + h
+    k[s] = spin_rhs(sp, w, m, ys);
+    ynew = ys;
+  }
   in.n_rhs += 6;
+  const double k1 = k[0], k3 = k[2], k4 = k[3], k5 = k[4], k6 = k[5], k7 = k[6];
   const double errv = h * fma(D::e7, k7, fma(D::e6, k6, fma(D::e5, k5, fma(D::e4, k4, fma(D::e3, k3, D::e1 * k1)))));
   const double sk = sp.rtol * fmax(fabs(y), fabs(ynew));
-  double err = fabs(errv) / sk;
-  if (!(err == err)) err = 1.0e10;            // NaN => reject and shrink
-  // PI controller (beta = 0.04), Hairer dopri5 defaults
-  const double beta = 0.04, expo1 = 0.2 - beta * 0.75, safe = 0.9, facc1 = 1.0 / 0.2, facc2 = 1.0 / 10.0;
-  const double fac11 = (err > 0.0) ? exp(log(err) * expo1) : 0.0;
-  double fac = fac11 * exp(-log(in.facold) * beta);
-  fac = fmax(facc2, fmin(facc1, fac / safe));
-  double hnew = h / fac;
-  if (err <= 1.0) {
-    in.facold = fmax(err, 1.0e-4);
+  const double aerr = fabs(errv);
+  const bool accept = aerr <= sk;                 // false for NaN
+  float errf = (float)aerr / (float)sk;
+  if (!(errf == errf)) errf = 1.0e10f;            // NaN => shrink hard
+  float fac11, fac;
+  controller(errf, in.facold, fac11, fac);
+  const float safe = 0.9f, facc1 = 5.0f, facc2 = 0.1f;   // h may shrink 5x, grow 10x
+  if (accept) {
+    fac = fmaxf(facc2, fminf(facc1, fac / safe));
+    double hnew = h / (double)fac;
+    in.facold = fmaxf(errf, 1.0e-4f);
     // dense output
     const double ydiff = ynew - y;
     const double bspl = fma(h, k1, -ydiff);
@@ -414,7 +526,7 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
     return true;
   }
   // rejected
-  hnew = h / fmin(facc1, fac11 / safe);
+  const double hnew = h / (double)fminf(facc1, fac11 / safe);
   in.h = hnew;
   in.rejected = 1;
   in.n_steps++;

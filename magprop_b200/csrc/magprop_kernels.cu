@@ -54,8 +54,14 @@ __device__ __forceinline__ void stage_theta(const double* __restrict__ theta, in
   __syncthreads();
 }
 
+#ifndef MP_MIN_BLOCKS_32
+#define MP_MIN_BLOCKS_32 16
+#endif
+#ifndef MP_MIN_BLOCKS_64
+#define MP_MIN_BLOCKS_64 8
+#endif
 template <int MODE, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) eval_kernel(const __grid_constant__ KernelArgs a) {
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64)) eval_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ double s_buf[kNB * BLOCK];
   __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
   stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta);

@@ -52,7 +52,7 @@ def test_model_lum_returns(built, golden):
     assert relerr(out[1:, g["node_index"]], g["lum_tight"][0]).max() < 5e-7
     x = tarr[[5, 700, 9000]]
     at = model_lum(g["pars"][0], xdata=x)
-    assert at.shape == (3,) and relerr(at, out[1, [5, 700, 9000]]).max() < 1e-12
+    assert at.shape == (3,) and relerr(at, out[1, [5, 700, 9000]]).max() < 1e-8
     with pytest.raises(ValueError):
         model_lum(g["pars"][0], xdata=[2.0e6])                               # interp1d bounds_error
     # kwargs reach the model (f_beam scales, n changes the propeller switch-on)
