@@ -198,7 +198,86 @@ struct Walker {
   int bad;         // non-finite / unphysical constants
 };
 
+// Accurate-but-slow x^(-1/7) (set-up code only).
 MP_HD double pow_m17(double x) { return exp(log(x) * (-1.0 / 7.0)); }
+
+// ---- hot-loop elementary functions -------------------------------------------------
+// Hand-rolled so that every polynomial coefficient is a constant-bank operand of
+// its DFMA (libdevice's exp/log materialise ~40 immediates per call, which showed
+// up as a quarter of all issued instructions in the first ncu profile).
+MP_CONST_QUALIFIER double kExpC[13] = {   // 1/n!, n = 0..12
+    1.0, 1.0, 1.0 / 2, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
+    1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600};
+MP_CONST_QUALIFIER double kExpR[4] = {1.4426950408889634074,      // log2(e)
+                                      6755399441055744.0,         // 2^52 + 2^51: round-to-nearest-integer shifter
+                                      -6.93147180369123816490e-01,  // -ln2 (high part)
+                                      -1.90821492927058770002e-10}; // -ln2 (low part)
+
+// exp(x) to ~2e-16 relative for x in [-708, 709]; below -708 returns ~1e-308 (callers
+// only ever multiply it by O(1e30) quantities that are already negligible there).
+MP_HD double exp_c(double x) {
+  double xc = (x < -708.0) ? -708.0 : x;
+  xc = (xc > 709.0) ? 709.0 : xc;
+  const double kd = fma(xc, kExpR[0], kExpR[1]);
+  const int k = (int)(dbits(kd) & 0xffffffffLL);
+  const double kf = kd - kExpR[1];
+  double r = fma(kf, kExpR[2], xc);
+  r = fma(kf, kExpR[3], r);
+  const double r2 = r * r;
+  double ev = kExpC[12], od = kExpC[11];
+  ev = fma(ev, r2, kExpC[10]);
+  od = fma(od, r2, kExpC[9]);
+  ev = fma(ev, r2, kExpC[8]);
+  od = fma(od, r2, kExpC[7]);
+  ev = fma(ev, r2, kExpC[6]);
+  od = fma(od, r2, kExpC[5]);
+  ev = fma(ev, r2, kExpC[4]);
+  od = fma(od, r2, kExpC[3]);
+  ev = fma(ev, r2, kExpC[2]);
+  od = fma(od, r2, kExpC[1]);
+  ev = fma(ev, r2, kExpC[0]);
+  const double p = fma(od, r, ev);
+  const double res = bitsd(dbits(p) + ((int64_t)k << 52));
+  return (x == x) ? res : x;
+}
+
+MP_CONST_QUALIFIER double kP17[9] = {   // m^(-1/7) on [1,2) in z = 2m - 3, 7.8e-9 relative
+    0x1.e32f899a660a5p-1, -0x1.70241e1493922p-5, 0x1.187cfebc0ad9ap-7, -0x1.0b37570227f94p-9,
+    0x1.17f49b665ef64p-11, -0x1.306c347674bdbp-13, 0x1.5b8846fafc617p-15, -0x1.fe4427ec39f39p-17,
+    0x1.314098ac46cb2p-18};
+MP_CONST_QUALIFIER double kP2b7[7] = {  // 2^(-b/7), b = 0..6
+    0x1.0000000000000p+0, 0x1.cfbb031a741a5p-1, 0x1.a402feeb9c533p-1, 0x1.7c6a1f29e2ce6p-1,
+    0x1.588cea3f093bep-1, 0x1.381147622f886p-1, 0x1.1aa59c4115e7ep-1};
+
+// x^(-1/7) for normal positive x to ~4e-16: exponent split e = 7a + b, polynomial
+// seed for the mantissa, one Newton step y += y (1 - m y^7) / 7.  NaN for x <= 0.
+MP_HD double pow_m17_fast(double x) {
+  const int64_t b = dbits(x);
+  const int e = (int)((b >> 52) & 0x7ff) - 1023;
+  const double m = bitsd((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const int ee = e + 1400;                 // positive for every normal exponent
+  const int a = ee / 7;
+  const int rem = ee - 7 * a;
+  const double z = fma(2.0, m, -3.0);
+  const double z2 = z * z;
+  double ev = kP17[8], od = kP17[7];
+  ev = fma(ev, z2, kP17[6]);
+  od = fma(od, z2, kP17[5]);
+  ev = fma(ev, z2, kP17[4]);
+  od = fma(od, z2, kP17[3]);
+  ev = fma(ev, z2, kP17[2]);
+  od = fma(od, z2, kP17[1]);
+  ev = fma(ev, z2, kP17[0]);
+  double y = fma(od, z, ev);
+  const double y2 = y * y, y4 = y2 * y2;
+  const double y7 = y4 * y2 * y;
+  y = fma(y * (1.0 / 7.0), fma(-m, y7, 1.0), y);
+  // scale by 2^(-(a-200)) * 2^(-rem/7)
+  const double sc = bitsd((int64_t)(1023 - (a - 200)) << 52);
+  const double res = y * kP2b7[rem] * sc;
+  const bool ok = (b > 0) && (((b >> 52) & 0x7ff) - 1 < 0x7fe);   // positive, normal, finite
+  return ok ? res : NAN;
+}
 
 MP_HD double rcp_fast(double x) {
 #if defined(__CUDA_ARCH__)
@@ -239,6 +318,7 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
     const double ua = fmax(w.u0 + 45.0, 1.0);
     const double ratio = fabs(w.C) * exp(w.u0 - ua) / (w.K * disc_S(ua));
     w.u_late = (ratio <= 1.0e-19) ? ua : ua + log(ratio * 1.0e19);
+    w.u_late -= 6.9;                         // transient <= 1e-16 of K*S (S falls only as a power law)
     w.Kq = pow_m17(w.K);
   }
   const double mu47 = exp(log(mu) * (4.0 / 7.0));
@@ -295,9 +375,9 @@ MP_HD DiscAt disc_at(const Walker& w, double t) {
     q = w.Kq * Q;
   } else {
     const double S = in ? poly10(ta.row, ta.s) : disc_S_outside(u, ta.e);
-    const double E = exp(w.u0 - u);
+    const double E = exp_c(w.u0 - u);
     M = fma(w.K, S, w.C * E);
-    q = pow_m17(M);
+    q = pow_m17_fast(M);
   }
   const double q2 = q * q;
   DiscAt d;
@@ -308,10 +388,10 @@ MP_HD DiscAt disc_at(const Walker& w, double t) {
   return d;
 }
 
-// tanh to 2e-16 absolute (the torque needs absolute, not relative, accuracy).
+// tanh to 4e-16 absolute (the torque needs absolute, not relative, accuracy).
 MP_HD double tanh_abs(double x) {
   if (x > 19.1) return 1.0;
-  const double e2 = exp(2.0 * x);
+  const double e2 = exp_c(2.0 * x);
   return fma(-2.0, rcp_fast(e2 + 1.0), 1.0);
 }
 
@@ -478,23 +558,39 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   bool last = false;
   if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
   const double tn = last ? t_end : t + h;
-  double k[7];
-  k[0] = in.k1;
+  const double k1 = in.k1;
+  double k2 = 0.0, k3 = 0.0, k4 = 0.0, k5 = 0.0, k6 = 0.0, k7 = 0.0;
   DiscAt m;
   double ynew = y;
+  // One inlined copy of f(t, omega) serves all six stages; the k's stay in registers
+  // (the switch is warp-uniform).
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
   for (int s = 1; s <= 6; ++s) {
-    double acc = kA[s][0] * k[0];
-    for (int j = 1; j < s; ++j) acc = fma(kA[s][j], k[j], acc);
+    double acc;
+    switch (s) {
+      case 1: acc = kA[1][0] * k1; break;
+      case 2: acc = fma(kA[2][1], k2, kA[2][0] * k1); break;
+      case 3: acc = fma(kA[3][2], k3, fma(kA[3][1], k2, kA[3][0] * k1)); break;
+      case 4: acc = fma(kA[4][3], k4, fma(kA[4][2], k3, fma(kA[4][1], k2, kA[4][0] * k1))); break;
+      case 5: acc = fma(kA[5][4], k5, fma(kA[5][3], k4, fma(kA[5][2], k3, fma(kA[5][1], k2, kA[5][0] * k1)))); break;
+      default: acc = fma(kA[6][5], k6, fma(kA[6][4], k5, fma(kA[6][3], k4, fma(kA[6][2], k3, kA[6][0] * k1)))); break;
+    }
     const double ys = fma(h, acc, y);
     if (s <= 5) m = disc_at(w, (s == 5) ? tn : fma(kCn[s], h, t));   // stage 7 reuses t_n + h
-    k[s] = spin_rhs(sp, w, m, ys);
+    const double f = spin_rhs(sp, w, m, ys);
+    switch (s) {
+      case 1: k2 = f; break;
+      case 2: k3 = f; break;
+      case 3: k4 = f; break;
+      case 4: k5 = f; break;
+      case 5: k6 = f; break;
+      default: k7 = f; break;
+    }
     ynew = ys;
   }
   in.n_rhs += 6;
-  const double k1 = k[0], k3 = k[2], k4 = k[3], k5 = k[4], k6 = k[5], k7 = k[6];
   const double errv = h * fma(D::e7, k7, fma(D::e6, k6, fma(D::e5, k5, fma(D::e4, k4, fma(D::e3, k3, D::e1 * k1)))));
   const double sk = sp.rtol * fmax(fabs(y), fabs(ynew));
   const double aerr = fabs(errv);
