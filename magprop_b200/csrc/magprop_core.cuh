@@ -29,7 +29,9 @@
 #if defined(__CUDACC__)
 #define MP_HD __host__ __device__ __forceinline__
 #define MP_TABLE_QUALIFIER __device__ const
-#define MP_CONST_QUALIFIER __constant__ const
+// NOT const on the device: a const __constant__ array with a visible initialiser is folded into
+// immediates, and every FP64 immediate costs two extra MOVs; a mutable one stays a c[3][..] operand.
+#define MP_CONST_QUALIFIER __constant__
 #else
 #define MP_CONST_QUALIFIER static const
 #define MP_HD inline
@@ -461,23 +463,20 @@ MP_HD Lum luminosity(const Spec& sp, const Walker& w, double M, double omega) {
 
 // ---- Dormand-Prince 5(4) with dense output --------------------------------
 // Coefficients: Dormand & Prince 1980; dense output: Hairer, Norsett & Wanner II.6.
-// Row s of kA gives stage s+1 from k1..ks; row 6 is the 5th-order weights (stage 7, FSAL).
-MP_CONST_QUALIFIER double kA[7][6] = {
-    {0, 0, 0, 0, 0, 0},
-    {1.0 / 5, 0, 0, 0, 0, 0},
-    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
-    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
-    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
-    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
-    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+// "Push" form: once k_j is known it is added straight into the running sums of the
+// stages that will use it, so no k_j has to be kept (no register shuffles, no local
+// memory).  Row j-1 holds, for source stage j = 1..7:
+//   [0..5]  a(j+1, j) ... a(j+6, j)   (stage 7 = the 5th-order weights b; 0 beyond it)
+//   [6]     e_j   (embedded error weights)        [7]  d_j  (dense-output weights)
+MP_CONST_QUALIFIER double kPush[7][8] = {
+    {1.0 / 5, 3.0 / 40, 44.0 / 45, 19372.0 / 6561, 9017.0 / 3168, 35.0 / 384, 71.0 / 57600, -12715105075.0 / 11282082432.0},
+    {9.0 / 40, -56.0 / 15, -25360.0 / 2187, -355.0 / 33, 0.0, 0.0, 0.0, 0.0},
+    {32.0 / 9, 64448.0 / 6561, 46732.0 / 5247, 500.0 / 1113, 0.0, 0.0, -71.0 / 16695, 87487479700.0 / 32700410799.0},
+    {-212.0 / 729, 49.0 / 176, 125.0 / 192, 0.0, 0.0, 0.0, 71.0 / 1920, -10690763975.0 / 1880347072.0},
+    {-5103.0 / 18656, -2187.0 / 6784, 0.0, 0.0, 0.0, 0.0, -17253.0 / 339200, 701980252875.0 / 199316789632.0},
+    {11.0 / 84, 0.0, 0.0, 0.0, 0.0, 0.0, 22.0 / 525, -1453857185.0 / 822651844.0},
+    {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, -1.0 / 40, 69997945.0 / 29380423.0}};
 MP_CONST_QUALIFIER double kCn[7] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1, 1};
-
-struct Dopri {
-  static constexpr double e1 = 71.0 / 57600, e3 = -71.0 / 16695, e4 = 71.0 / 1920, e5 = -17253.0 / 339200, e6 = 22.0 / 525, e7 = -1.0 / 40;
-  static constexpr double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0,
-                          d4 = -10690763975.0 / 1880347072.0, d5 = 701980252875.0 / 199316789632.0,
-                          d6 = -1453857185.0 / 822651844.0, d7 = 69997945.0 / 29380423.0;
-};
 
 // State of the spin integration of one walker.
 struct Integrator {
@@ -552,46 +551,40 @@ MP_HD void controller(float err, float facold, float& fac11, float& fac) {
 // Attempt one step; on acceptance advances (t, omega) and refreshes the dense
 // output.  Returns true when a step was accepted.
 MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
-  using D = Dopri;
   const double t = in.t, y = in.omega;
   double h = in.h;
   bool last = false;
   if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
   const double tn = last ? t_end : t + h;
   const double k1 = in.k1;
-  double k2 = 0.0, k3 = 0.0, k4 = 0.0, k5 = 0.0, k6 = 0.0, k7 = 0.0;
+  // running sums for the next six stages, the error estimate and the dense output
+  double a0 = kPush[0][0] * k1, a1 = kPush[0][1] * k1, a2 = kPush[0][2] * k1, a3 = kPush[0][3] * k1,
+         a4 = kPush[0][4] * k1, a5 = kPush[0][5] * k1;
+  double esum = kPush[0][6] * k1, dsum = kPush[0][7] * k1;
   DiscAt m;
-  double ynew = y;
-  // One inlined copy of f(t, omega) serves all six stages; the k's stay in registers
-  // (the switch is warp-uniform).
+  double ynew = y, k7 = k1;
+  // One inlined copy of f(t, omega) serves all six stage evaluations.
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
   for (int s = 1; s <= 6; ++s) {
-    double acc;
-    switch (s) {
-      case 1: acc = kA[1][0] * k1; break;
-      case 2: acc = fma(kA[2][1], k2, kA[2][0] * k1); break;
-      case 3: acc = fma(kA[3][2], k3, fma(kA[3][1], k2, kA[3][0] * k1)); break;
-      case 4: acc = fma(kA[4][3], k4, fma(kA[4][2], k3, fma(kA[4][1], k2, kA[4][0] * k1))); break;
-      case 5: acc = fma(kA[5][4], k5, fma(kA[5][3], k4, fma(kA[5][2], k3, fma(kA[5][1], k2, kA[5][0] * k1)))); break;
-      default: acc = fma(kA[6][5], k6, fma(kA[6][4], k5, fma(kA[6][3], k4, fma(kA[6][2], k3, kA[6][0] * k1)))); break;
-    }
-    const double ys = fma(h, acc, y);
+    const double ys = fma(h, a0, y);
     if (s <= 5) m = disc_at(w, (s == 5) ? tn : fma(kCn[s], h, t));   // stage 7 reuses t_n + h
     const double f = spin_rhs(sp, w, m, ys);
-    switch (s) {
-      case 1: k2 = f; break;
-      case 2: k3 = f; break;
-      case 3: k4 = f; break;
-      case 4: k5 = f; break;
-      case 5: k6 = f; break;
-      default: k7 = f; break;
-    }
+    const double* c = kPush[s];
+    a0 = fma(c[0], f, a1);
+    a1 = fma(c[1], f, a2);
+    a2 = fma(c[2], f, a3);
+    a3 = fma(c[3], f, a4);
+    a4 = fma(c[4], f, a5);
+    a5 = 0.0;
+    esum = fma(c[6], f, esum);
+    dsum = fma(c[7], f, dsum);
     ynew = ys;
+    k7 = f;
   }
   in.n_rhs += 6;
-  const double errv = h * fma(D::e7, k7, fma(D::e6, k6, fma(D::e5, k5, fma(D::e4, k4, fma(D::e3, k3, D::e1 * k1)))));
+  const double errv = h * esum;
   const double sk = sp.rtol * fmax(fabs(y), fabs(ynew));
   const double aerr = fabs(errv);
   const bool accept = aerr <= sk;                 // false for NaN
@@ -611,7 +604,7 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
     in.r2 = ydiff;
     in.r3 = bspl;
     in.r4 = ydiff - h * k7 - bspl;
-    in.r5 = h * fma(D::d7, k7, fma(D::d6, k6, fma(D::d5, k5, fma(D::d4, k4, fma(D::d3, k3, D::d1 * k1)))));
+    in.r5 = h * dsum;
     in.t0 = t; in.hs = h; in.t1 = tn;
     in.t = tn;
     in.omega = ynew;
