@@ -342,6 +342,35 @@ def extras(args, liks, data, dev, rank, world, torch, O, A):
         out[f"ball_1e-4_W{W}"] = timed(truth + 1e-4 * rng.randn(W, 6))
     out["posterior_spread_0.05_W262144"] = timed(np.clip(truth + 0.05 * rng.randn(1 << 18, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER))
     out["prior_uniform_W65536"] = timed(rng.uniform(O.SCRIPT_LOWER, O.SCRIPT_UPPER, size=(1 << 16, 6)), reps=1)
+
+    # ---- fused on-device stretch move (one launch per half-step) -------------------------------
+    from magprop_b200.sampler import DeviceEnsemble
+    import torch.distributed as dist
+
+    def mcmc(nwalk, nsteps, use_dist):
+        g = np.random.RandomState(7)          # same start on every rank (the ensemble is replicated)
+        ens = DeviceEnsemble.from_likelihood(lk, nwalk, 6, a=2.0, seed=2017, dist=dist if use_dist else None)
+        ens.initialise(truth + 1e-4 * g.randn(nwalk, 6))
+        ens.run(2)
+        torch.cuda.synchronize()
+        if use_dist and world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ens.run(nsteps)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if use_dist and world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        return {"nwalkers": nwalk, "steps": nsteps, "ms_per_step": ms / nsteps, "mcmc_steps_per_s": nsteps / ms * 1e3,
+                "evals_per_s": nwalk * nsteps / ms * 1e3, "acceptance": float(ens.acceptance_fraction().mean().item()),
+                "ranks": world if use_dist else 1}
+
+    out["mcmc_config2_nwalk256_fused_stretch"] = mcmc(256, 50, False)
+    big = (1 << 18) * world
+    out[f"mcmc_nwalk{big}_fused_stretch_allgather" if world > 1 else f"mcmc_nwalk{big}_fused_stretch"] = mcmc(big, 5, True)
     return out
 
 

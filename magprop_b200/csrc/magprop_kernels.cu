@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(BLOCK) stretch_kernel(const __grid_constant__ 
   const double uz = u01(r0.c[0], r0.c[1]);
   const double up = u01(r0.c[2], r0.c[3]);
   const double ua = u01(r1.c[0], r1.c[1]);
-  const double zr = (s.a - 1.0) * uz + 1.0;
-  const double z = zr * zr / s.a;
+  const double zr = __dadd_rn(__dmul_rn(s.a - 1.0, uz), 1.0);
+  const double z = __ddiv_rn(__dmul_rn(zr, zr), s.a);
   int pj = (int)(up * s.n_complement);
   if (pj >= s.n_complement) pj = s.n_complement - 1;
   const int partner = s.complement[pj];
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(BLOCK) stretch_kernel(const __grid_constant__ 
   for (int d = 0; d < ndim; ++d) {
     const double c = s.coords[(size_t)partner * ndim + d];
     const double x = s.coords[(size_t)me * ndim + d];
-    q[d] = c - (c - x) * z;
+    q[d] = __dadd_rn(c, -__dmul_rn(__dadd_rn(c, -x), z));   // no FMA contraction: reproducible on the host
   }
   int st = kWalkerOk, nr = 0;
   double lp_new = -INFINITY;
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(BLOCK) stretch_kernel(const __grid_constant__ 
     lp_new = ll;
   }
   const double lp_old = s.lnp[me];
-  const double lnpdiff = (ndim - 1.0) * log(z) + lp_new - lp_old;
+  const double lnpdiff = __dadd_rn(__dadd_rn(__dmul_rn(ndim - 1.0, log(z)), lp_new), -lp_old);
   if (lnpdiff > log(ua)) {
     for (int d = 0; d < ndim; ++d) s.coords[(size_t)me * ndim + d] = q[d];
     s.lnp[me] = lp_new;
