@@ -56,6 +56,7 @@ constexpr int kWalkerPriorReject = 1;
 constexpr int kWalkerIntegratorFail = 2;
 constexpr int kWalkerNonfiniteState = 4;
 constexpr int kWalkerNonfiniteLnlike = 8;
+constexpr int kWalkerDeferred = 16;   // internal: handed to the stiff-capable launch
 
 // Device-side copy of mp_model_spec plus derived walker-independent constants.
 struct Spec {
@@ -71,6 +72,7 @@ struct Spec {
   int lprop_binding_term;
   int unlog_mask;
   double rtol;
+  double rtol_stiff;           // tolerance of the Radau error estimate
   int max_steps;
 };
 
@@ -421,6 +423,54 @@ MP_HD double spin_rhs(const Spec& sp, const Walker& w, const DiscAt& d, double o
   return fma(-w.Cdip_I * om2, omega, nacc * sp.inv_inertia);
 }
 
+// Break-up sliding mode.  N_acc is switched off above rot_param = breakup_rhs (funcs.py:131-132).
+// If the spin reaches that boundary while the accretion torque still outweighs the dipole torque,
+// the solution chatters across the discontinuity (a Filippov sliding mode): LSODA burns its step
+// budget there and the reference returns 'flag' -> -inf (funcs.py:172-173).  We detect the
+// crossing and fail at once instead of taking 1e5 tiny steps to the same verdict.
+MP_HD bool breakup_sliding(const Spec& sp, const Walker& w, const DiscAt& d, double y_old, double y_new);
+
+// f and J = df/d(omega) together (implicit stages of the stiff integrator).
+MP_HD void spin_rhs_jac(const Spec& sp, const Walker& w, const DiscAt& d, double omega, double& f, double& J) {
+  double fast, lever, dfast, dlever;
+  if (d.rm * omega >= w.kc) {
+    const double r = rsqrt_fast(omega);
+    const double hio = -0.5 * r * r;                 // -1/(2 omega)
+    fast = w.Ccap * r;
+    dfast = fast * hio;
+    if (w.kc >= kR * omega) { lever = w.sGMkc * r; dlever = lever * hio; }
+    else { lever = sp.sqrt_GMR; dlever = 0.0; }
+  } else {
+    fast = d.wq * omega;
+    dfast = d.wq;
+    lever = (d.rm >= kR) ? w.sGMA * d.q : sp.sqrt_GMR;
+    dlever = 0.0;
+  }
+  const double om2 = omega * omega;
+  double nacc = 0.0, dnacc = 0.0;
+  if (!(om2 > sp.omega2_breakup_rhs)) {
+    const double x = sp.rhs_n * (fast - 1.0);
+    double th = 1.0, sech2 = 0.0;
+    if (!(x > 19.1)) {
+      const double r = rcp_fast(exp_c(2.0 * x) + 1.0);
+      th = fma(-2.0, r, 1.0);
+      sech2 = 4.0 * r * (1.0 - r);
+    }
+    nacc = -lever * d.mdot * th;
+    dnacc = -d.mdot * fma(dlever, th, lever * sp.rhs_n * sech2 * dfast);
+  }
+  f = fma(-w.Cdip_I * om2, omega, nacc * sp.inv_inertia);
+  J = fma(-3.0 * w.Cdip_I, om2, dnacc * sp.inv_inertia);
+}
+
+MP_HD bool breakup_sliding(const Spec& sp, const Walker& w, const DiscAt& d, double y_old, double y_new) {
+  const bool above_old = y_old * y_old > sp.omega2_breakup_rhs;
+  const bool above_new = y_new * y_new > sp.omega2_breakup_rhs;
+  if (above_old == above_new) return false;
+  const double om_c = sqrt(sp.omega2_breakup_rhs) * (1.0 - 1.0e-12);   // just inside: N_acc on
+  return spin_rhs(sp, w, d, om_c) > 0.0;
+}
+
 // Luminosity stage at one node (erg/s, not yet /1e50): funcs.py:175-229.
 struct Lum { double tot, prop, dip; };
 
@@ -486,6 +536,9 @@ struct Integrator {
   // dense output of the last accepted step: omega(t0 + theta*hs)
   double t0, hs, r1, r2, r3, r4, r5, t1;
   int n_rhs, n_steps, status;
+  // stiffness switch: DP5 <-> Radau IIA
+  int stiff;                     // 1: take implicit steps
+  int stiff_votes;               // consecutive steps voting to change mode
 };
 
 MP_HD double dense_eval(const Integrator& in, double tq) {
@@ -511,6 +564,8 @@ MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, doub
   in.facold = 1.0e-4f;
   in.rejected = 0;
   in.n_steps = 0;
+  in.stiff = 0;
+  in.stiff_votes = 0;
   in.status = kWalkerOk;
   in.t0 = t_start; in.t1 = t_start; in.hs = 1.0;
   in.r1 = w.omega0; in.r2 = in.r3 = in.r4 = in.r5 = 0.0;
@@ -562,14 +617,15 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
          a4 = kPush[0][4] * k1, a5 = kPush[0][5] * k1;
   double esum = kPush[0][6] * k1, dsum = kPush[0][7] * k1;
   DiscAt m;
-  double ynew = y, k7 = k1;
-  // One inlined copy of f(t, omega) serves all six stage evaluations.
+  double y6 = y, k6 = k1;
+  // One inlined copy of disc_at + f serves the five stages that need a new time; the FSAL
+  // stage (k7, same time as stage 6) is peeled so that nothing extra stays live in the loop.
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-  for (int s = 1; s <= 6; ++s) {
+  for (int s = 1; s <= 5; ++s) {
     const double ys = fma(h, a0, y);
-    if (s <= 5) m = disc_at(w, (s == 5) ? tn : fma(kCn[s], h, t));   // stage 7 reuses t_n + h
+    m = disc_at(w, (s == 5) ? tn : fma(kCn[s], h, t));
     const double f = spin_rhs(sp, w, m, ys);
     const double* c = kPush[s];
     a0 = fma(c[0], f, a1);
@@ -580,9 +636,13 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
     a5 = 0.0;
     esum = fma(c[6], f, esum);
     dsum = fma(c[7], f, dsum);
-    ynew = ys;
-    k7 = f;
+    y6 = ys;
+    k6 = f;
   }
+  const double ynew = fma(h, a0, y);
+  const double k7 = spin_rhs(sp, w, m, ynew);
+  esum = fma(kPush[6][6], k7, esum);
+  dsum = fma(kPush[6][7], k7, dsum);
   in.n_rhs += 6;
   const double errv = h * esum;
   const double sk = sp.rtol * fmax(fabs(y), fabs(ynew));
@@ -609,9 +669,25 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
     in.t = tn;
     in.omega = ynew;
     in.k1 = k7;
+#ifndef MP_NO_SLIDING
+    if (breakup_sliding(sp, w, m, y, ynew)) in.status = kWalkerIntegratorFail;
+#endif
     in.h = in.rejected ? fmin(hnew, h) : hnew;
     in.rejected = 0;
     in.n_steps++;
+    // stiffness detection: h*|lambda| estimated from the last two stages, which share t_n + h
+    // (Hairer's dopri5 device).  The controller holds a stiff walker near h*|lambda| ~ 2 (the error
+    // estimate grows before the stability limit 3.3 is reached), i.e. at steps far smaller than
+    // the time scale t on which the solution itself varies.  12 such steps in a row hand the
+    // walker to the implicit integrator.
+#ifndef MP_NO_VOTES
+    const double dy = fabs(ynew - y6);
+    if (fabs(k7 - k6) * tn > 30.0 * dy && h < 0.02 * tn) {   // |lambda| t > 30 while h << t
+      if (++in.stiff_votes >= 12) { in.stiff = 1; in.stiff_votes = 0; }
+    } else {
+      in.stiff_votes = 0;
+    }
+#endif
     return true;
   }
   // rejected
@@ -621,6 +697,141 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   in.n_steps++;
   if (!(fabs(hnew) > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
   return false;
+}
+
+// ---- Radau IIA (order 5) for the stiff phases -------------------------------------
+// When much mass flows, the spin is pinned to the propeller/accretion equilibrium
+// w = 1 by the steep tanh(n(w-1)) (relaxation rate 0.1..1 /s against t up to 1e6 s;
+// SURVEY.md fact 4) and DP5 becomes stability-bound.  The equation is scalar, so a
+// fully implicit 3-stage Radau IIA step is a 3x3 Newton solve with an analytic
+// Jacobian -- no linear algebra library, no Jacobian storage.
+//   stages  Z_i = h sum_j a_ij f(t + c_j h, y + Z_j),   y_{n+1} = y_n + Z_3
+//   error   (f0 + (dd . Z)/h) / (u1/h - J0)            (Hairer & Wanner IV.8)
+//   dense   the cubic collocation polynomial, stored in the DP5 dense form (r5 = 0)
+struct RadauC {
+  static constexpr double s6 = 2.449489742783178098197284;
+  static constexpr double c1 = (4.0 - s6) / 10.0, c2 = (4.0 + s6) / 10.0;
+  static constexpr double a11 = (88.0 - 7.0 * s6) / 360.0, a12 = (296.0 - 169.0 * s6) / 1800.0, a13 = (-2.0 + 3.0 * s6) / 225.0;
+  static constexpr double a21 = (296.0 + 169.0 * s6) / 1800.0, a22 = (88.0 + 7.0 * s6) / 360.0, a23 = (-2.0 - 3.0 * s6) / 225.0;
+  static constexpr double a31 = (16.0 - s6) / 36.0, a32 = (16.0 + s6) / 36.0, a33 = 1.0 / 9.0;
+  static constexpr double u1 = 3.6378342527444957322;     // 30 / (6 + 81^(1/3) - 9^(1/3))
+  static constexpr double dd1 = -(13.0 + 7.0 * s6) / 3.0, dd2 = (-13.0 + 7.0 * s6) / 3.0, dd3 = -1.0 / 3.0;
+};
+
+#if defined(__CUDACC__)
+__device__ __host__ __noinline__
+#endif
+static Integrator radau_step(const Spec sp, const Walker w, double t_end, Integrator in) {
+  // Everything by value: a reference here would pin the caller's Integrator/Walker to local
+  // memory for the whole kernel, slowing the explicit path that never comes here.
+  using R = RadauC;
+  const double t = in.t, y = in.omega;
+  double h = in.h;
+  bool last = false;
+  if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
+  const double tn = last ? t_end : t + h;
+  const DiscAt m0 = disc_at(w, t);
+  const DiscAt m1 = disc_at(w, fma(R::c1, h, t));
+  const DiscAt m2 = disc_at(w, fma(R::c2, h, t));
+  const DiscAt m3 = disc_at(w, tn);
+  double f0, J0;
+  spin_rhs_jac(sp, w, m0, y, f0, J0);
+  in.n_rhs += 1;
+  const double sk = sp.rtol * fabs(y);
+  // starting values: extrapolate the previous step's dense polynomial
+  double z1 = dense_eval(in, fma(R::c1, h, t)) - y;
+  double z2 = dense_eval(in, fma(R::c2, h, t)) - y;
+  double z3 = dense_eval(in, tn) - y;
+  if (!(fabs(z3) < 0.5 * fabs(y)) || in.rejected) { z1 = z2 = z3 = 0.0; }
+  bool converged = false;
+  double dz_prev = INFINITY;
+  int it = 0;
+  for (; it < 8; ++it) {
+    double f1, f2, f3, J1, J2, J3;
+    spin_rhs_jac(sp, w, m1, y + z1, f1, J1);
+    spin_rhs_jac(sp, w, m2, y + z2, f2, J2);
+    spin_rhs_jac(sp, w, m3, y + z3, f3, J3);
+    in.n_rhs += 3;
+    // residual G = Z - h A f
+    const double g1 = z1 - h * (R::a11 * f1 + R::a12 * f2 + R::a13 * f3);
+    const double g2 = z2 - h * (R::a21 * f1 + R::a22 * f2 + R::a23 * f3);
+    const double g3 = z3 - h * (R::a31 * f1 + R::a32 * f2 + R::a33 * f3);
+    // Newton matrix M = I - h A diag(J)
+    const double h1 = h * J1, h2 = h * J2, h3 = h * J3;
+    const double m11 = 1.0 - R::a11 * h1, m12 = -R::a12 * h2, m13 = -R::a13 * h3;
+    const double m21 = -R::a21 * h1, m22 = 1.0 - R::a22 * h2, m23 = -R::a23 * h3;
+    const double m31 = -R::a31 * h1, m32 = -R::a32 * h2, m33 = 1.0 - R::a33 * h3;
+    // solve M d = -G by Cramer's rule
+    const double c11 = m22 * m33 - m23 * m32, c12 = m23 * m31 - m21 * m33, c13 = m21 * m32 - m22 * m31;
+    const double det = m11 * c11 + m12 * c12 + m13 * c13;
+    if (!(fabs(det) > 1.0e-300)) break;
+    const double idet = -1.0 / det;
+    const double d1 = idet * (g1 * c11 + g2 * (m13 * m32 - m12 * m33) + g3 * (m12 * m23 - m13 * m22));
+    const double d2 = idet * (g1 * c12 + g2 * (m11 * m33 - m13 * m31) + g3 * (m13 * m21 - m11 * m23));
+    const double d3 = idet * (g1 * c13 + g2 * (m12 * m31 - m11 * m32) + g3 * (m11 * m22 - m12 * m21));
+    z1 += d1; z2 += d2; z3 += d3;
+    const double dz = fmax(fabs(d1), fmax(fabs(d2), fabs(d3)));
+    if (!(dz == dz)) break;
+    if (dz <= 1.0e-3 * sk + 4.0e-16 * fabs(z3)) { converged = true; ++it; break; }
+    if (it >= 2 && dz > 2.0 * dz_prev) break;      // diverging
+    dz_prev = dz;
+  }
+  in.n_steps++;
+  if (!converged) {
+    in.h = 0.5 * h;
+    in.rejected = 1;
+    if (!(in.h > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
+    return in;
+  }
+  const double ynew = y + z3;
+  // The embedded estimate is O(h^4) for an O(h^6) local error, so it is held to rtol_stiff
+  // (~ rtol^(2/3)), not rtol; the parity tests bound the resulting error.
+  const double skn = sp.rtol_stiff * fmax(fabs(y), fabs(ynew));
+  const double ih = 1.0 / h;
+  const double comb = (R::dd1 * z1 + R::dd2 * z2 + R::dd3 * z3) * ih;
+  const double den = R::u1 * ih - J0;
+  double errv = (f0 + comb) / den;
+  double err = fabs(errv) / skn;
+  if (err >= 1.0 && (in.rejected || in.n_steps <= 1)) {
+    double fe, Je;
+    spin_rhs_jac(sp, w, m0, y + errv, fe, Je);
+    in.n_rhs += 1;
+    errv = (fe + comb) / den;
+    err = fabs(errv) / skn;
+  }
+  if (!(err == err)) err = 1.0e10;
+  // step-size selection (radau5): order-3 estimate, safety tied to the Newton effort
+  const double safe = 0.9, fac = fmin(safe, safe * 15.0 / (double)(7 + 2 * it));
+  double quot = fmax(0.125, fmin(5.0, exp(0.25 * log(fmax(err, 1.0e-30))) / fac));
+  const double hnew = h / quot;
+  if (err < 1.0) {
+    // collocation cubic through (0,0), (c1,z1), (c2,z2), (1,z3) in the DP5 dense form
+    const double g1 = (z1 / R::c1 - z3) / (1.0 - R::c1);
+    const double g2 = (z2 / R::c2 - z3) / (1.0 - R::c2);
+    const double r4 = (g2 - g1) / (R::c2 - R::c1);
+    in.r1 = y; in.r2 = z3; in.r3 = g1 - R::c1 * r4; in.r4 = r4; in.r5 = 0.0;
+    in.t0 = t; in.hs = h; in.t1 = tn;
+    in.t = tn;
+    in.omega = ynew;
+    double fn, Jn;
+    spin_rhs_jac(sp, w, m3, ynew, fn, Jn);
+    in.n_rhs += 1;
+    in.k1 = fn;                                     // keeps DP5's FSAL slot valid for a switch back
+    if (breakup_sliding(sp, w, m3, y, ynew)) in.status = kWalkerIntegratorFail;
+    in.h = in.rejected ? fmin(hnew, h) : hnew;
+    in.rejected = 0;
+    // hand back to the explicit integrator once the step is no longer stability-relevant
+    if (h * fabs(Jn) < 0.5) {
+      if (++in.stiff_votes >= 4) { in.stiff = 0; in.stiff_votes = 0; in.facold = 1.0e-4f; }
+    } else {
+      in.stiff_votes = 0;
+    }
+    return in;
+  }
+  in.h = hnew;
+  in.rejected = 1;
+  if (!(fabs(hnew) > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
+  return in;
 }
 
 // ---- parameter handling -------------------------------------------------------
@@ -672,7 +883,11 @@ enum EvalMode { kModeLnprob = 0, kModeModelAtData = 1, kModeCurves = 2 };
 //   kModeModelAtData : out[dat_orig[i]*ostride] = model at sorted datum i (/1e50)
 //   kModeCurves      : out[(c*Gs + j)*ostride]  = Ltot,Lprop,Ldip (c=0,1,2) at node j (/1e50)
 //                      state_out[(c*Gs + j)*ostride] = Mdisc, omega (optional)
-template <int MODE, int NB>
+// STIFF = false builds the explicit-only variant: a walker whose spin equation turns stiff is
+// not integrated implicitly here but returned with kWalkerDeferred, to be re-run by the
+// STIFF = true variant (the kernels bucket such walkers into a second launch, so the common
+// explicit path is compiled without the implicit integrator's register and stack footprint).
+template <int MODE, int NB, bool STIFF>
 MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w, double* buf,
                              int bstride, int& status, int& n_rhs, double* out,
                              double* state_out, int ostride, const int* dat_orig) {
@@ -705,6 +920,14 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
         } else if (in.status != kWalkerOk) {
           buf[(jn - c0) * bstride] = NAN;
           ++jn;
+        } else if (in.stiff) {
+          if (STIFF) {
+            in = radau_step(sp, w, t_end, in);
+          } else {
+            status |= kWalkerDeferred;
+            n_rhs = in.n_rhs;
+            return 0.0;
+          }
         } else {
           integrator_step(sp, w, t_end, in);
         }

@@ -37,6 +37,8 @@ struct KernelArgs {
   int* n_rhs;           // [W] or null
   double* out;          // mode-dependent
   double* state;        // curves: [W][2][Gs] or null
+  int* queue;           // [W] walkers deferred to the stiff launch
+  int* queue_count;     // [1]
 };
 
 // Coalesced load of this block's walker parameters into shared memory
@@ -60,15 +62,10 @@ __device__ __forceinline__ void stage_theta(const double* __restrict__ theta, in
 #ifndef MP_MIN_BLOCKS_64
 #define MP_MIN_BLOCKS_64 8
 #endif
-template <int MODE, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64)) eval_kernel(const __grid_constant__ KernelArgs a) {
-  __shared__ double s_buf[kNB * BLOCK];
-  __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
-  stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta);
-  const int w = blockIdx.x * BLOCK + threadIdx.x;
-  if (w >= a.W) return;
-  const double* th = s_theta + threadIdx.x * a.ndim;
 
+// One walker, end to end.  Returns true when the walker was deferred to the stiff launch.
+template <int MODE, int BLOCK, bool STIFF>
+__device__ __forceinline__ bool eval_one(const KernelArgs& a, int w, const double* th, double* s_buf) {
   int st = kWalkerOk, nr = 0;
   double result = -INFINITY;
   if (a.prior_enabled && !prior_accepts(th, a.ndim, a.lower, a.upper)) {
@@ -86,8 +83,9 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MI
     } else if (MODE == kModeModelAtData) {
       out = a.out + (size_t)w * a.dv.n_data;
     }
-    const double chi2 = evaluate_walker<MODE, kNB>(a.sp, a.dv, wk, s_buf + threadIdx.x, BLOCK, st, nr,
-                                                   out, state, 1, a.dat_orig);
+    const double chi2 = evaluate_walker<MODE, kNB, STIFF>(a.sp, a.dv, wk, s_buf + threadIdx.x, BLOCK, st, nr,
+                                                          out, state, 1, a.dat_orig);
+    if (!STIFF && (st & kWalkerDeferred)) return true;
     if (MODE == kModeLnprob) {
       double ll = -0.5 * chi2;                     // mcmc_eqns.py:25
       if (st & kWalkerIntegratorFail) {
@@ -102,6 +100,33 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MI
   if (MODE == kModeLnprob) a.lnp[w] = result;
   if (a.status) a.status[w] = st;
   if (a.n_rhs) a.n_rhs[w] = nr;
+  return false;
+}
+
+// Main launch: explicit integrator only; stiff walkers are pushed onto a queue.
+template <int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64))
+eval_kernel(const __grid_constant__ KernelArgs a) {
+  __shared__ double s_buf[kNB * BLOCK];
+  __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
+  stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta);
+  const int w = blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= a.W) return;
+  if (eval_one<MODE, BLOCK, false>(a, w, s_theta + threadIdx.x * a.ndim, s_buf))
+    a.queue[atomicAdd(a.queue_count, 1)] = w;
+}
+
+// Second launch: the walkers bucketed as stiff, with the implicit integrator available.
+template <int MODE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) eval_stiff_kernel(const __grid_constant__ KernelArgs a) {
+  __shared__ double s_buf[kNB * BLOCK];
+  const int n = *a.queue_count;
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
+    const int w = a.queue[i];
+    double th[MP_MAX_NDIM];
+    for (int d = 0; d < a.ndim; ++d) th[d] = a.theta[(size_t)w * a.ndim + d];
+    eval_one<MODE, BLOCK, true>(a, w, th, s_buf);
+  }
 }
 
 // ---- counter-based RNG: Philox4x32-10 (Salmon et al. 2011) -------------------
@@ -144,14 +169,11 @@ struct StretchArgs {
 
 // One emcee StretchMove half-step (Goodman & Weare 2010; emcee RedBlueMove):
 //   z = ((a-1) u + 1)^2 / a ; q = c - (c - s) z ; accept iff (ndim-1) ln z + lp(q) - lp(s) > ln u'
-// fused with the likelihood so a half-step is one launch.
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) stretch_kernel(const __grid_constant__ StretchArgs s) {
-  __shared__ double s_buf[kNB * BLOCK];
+// fused with the likelihood so a half-step is one launch (plus the stiff-bucket launch, which
+// finds an empty queue for ensembles near the synthetic truths).  Returns true when deferred.
+template <int BLOCK, bool STIFF>
+__device__ __forceinline__ bool stretch_one(const StretchArgs& s, int me, double* s_buf) {
   const KernelArgs& a = s.k;
-  const int i = blockIdx.x * BLOCK + threadIdx.x;
-  if (i >= s.n_active) return;
-  const int me = s.active[i];
   const int ndim = a.ndim;
   // counter = (step, walker); two Philox blocks give u_z, u_partner, u_accept
   const Philox r0 = philox4x32_10((uint32_t)s.step, (uint32_t)(s.step >> 32), (uint32_t)me, 0u,
@@ -179,8 +201,9 @@ __global__ void __launch_bounds__(BLOCK) stretch_kernel(const __grid_constant__ 
     unpack_theta(a.sp, q, ndim, pars, dipeff, propeff, f_beam);
     Walker wk;
     walker_setup(a.sp, pars, dipeff, propeff, f_beam, a.dv.t_start, wk);
-    const double chi2 = evaluate_walker<kModeLnprob, kNB>(a.sp, a.dv, wk, s_buf + threadIdx.x, BLOCK, st,
-                                                          nr, nullptr, nullptr, 1, nullptr);
+    const double chi2 = evaluate_walker<kModeLnprob, kNB, STIFF>(a.sp, a.dv, wk, s_buf + threadIdx.x, BLOCK, st,
+                                                                 nr, nullptr, nullptr, 1, nullptr);
+    if (!STIFF && (st & kWalkerDeferred)) return true;
     double ll = -0.5 * chi2;
     if ((st & kWalkerIntegratorFail) || !isfinite(ll)) ll = -INFINITY;
     lp_new = ll;
@@ -193,6 +216,25 @@ __global__ void __launch_bounds__(BLOCK) stretch_kernel(const __grid_constant__ 
     if (s.accepted) s.accepted[me] += 1;
   }
   if (a.n_rhs) a.n_rhs[me] = nr;
+  return false;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64))
+stretch_kernel(const __grid_constant__ StretchArgs s) {
+  __shared__ double s_buf[kNB * BLOCK];
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= s.n_active) return;
+  const int me = s.active[i];
+  if (stretch_one<BLOCK, false>(s, me, s_buf)) s.k.queue[atomicAdd(s.k.queue_count, 1)] = me;
+}
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) stretch_stiff_kernel(const __grid_constant__ StretchArgs s) {
+  __shared__ double s_buf[kNB * BLOCK];
+  const int n = *s.k.queue_count;
+  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK)
+    stretch_one<BLOCK, true>(s, s.k.queue[i], s_buf);
 }
 
 // ---- the coupled right-hand side, as ODEs()/odes() return it -----------------------
@@ -293,6 +335,10 @@ struct mp_handle {
   double *s_theta = nullptr, *s_out = nullptr, *s_state = nullptr, *s_lnp = nullptr;
   int *s_status = nullptr, *s_nrhs = nullptr;
   size_t cap_theta = 0, cap_out = 0, cap_state = 0, cap_w = 0;
+  int* d_queue = nullptr;      // walkers deferred to the stiff launch
+  int* d_queue_count = nullptr;
+  size_t cap_queue = 0;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
 };
 
@@ -350,6 +396,14 @@ extern "C" int mp_create(const mp_model_spec* spec, const mp_prior_spec* prior, 
   if (prior) h->prior = *prior;
   else std::memset(&h->prior, 0, sizeof(h->prior));
   h->grid.assign(grid, grid + G);
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  }
+  if (cudaMalloc((void**)&h->d_queue_count, sizeof(int)) != cudaSuccess) {
+    delete h;
+    return fail(MP_ERR_CUDA, "mp_create: cudaMalloc failed");
+  }
   h->D = D;
   h->np = np;
   h->data_nodes.n_nodes = (int)np.node_t.size();
@@ -373,6 +427,7 @@ extern "C" void mp_destroy(mp_handle* h) {
   for (auto& kv : h->curve_nodes) cudaFree(kv.second.node_t);
   cudaFree(h->s_theta); cudaFree(h->s_out); cudaFree(h->s_state); cudaFree(h->s_lnp);
   cudaFree(h->s_status); cudaFree(h->s_nrhs);
+  cudaFree(h->d_queue); cudaFree(h->d_queue_count);
   delete h;
 }
 
@@ -412,14 +467,35 @@ static int fill_args(mp_handle* h, KernelArgs& a, const DeviceNodes& nodes, bool
   return MP_OK;
 }
 
+static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream) {
+  int rc = ensure(&h->d_queue, &h->cap_queue, (size_t)W);
+  if (rc) return rc;
+  a.queue = h->d_queue;
+  a.queue_count = h->d_queue_count;
+  MP_CUDA(cudaMemsetAsync(h->d_queue_count, 0, sizeof(int), stream));
+  return MP_OK;
+}
+
+// grid of the stiff-bucket launch: grid-stride over a queue whose length is only known on the
+// device; a few blocks per SM are enough to cover it (it exits at once when the queue is empty)
+static int stiff_grid(const mp_handle* h, int W, int block) {
+  const int full = (W + block - 1) / block;
+  const int cap = h->sm_count * 8;
+  return full < cap ? full : cap;
+}
+
 template <int MODE>
-static int launch_eval(const KernelArgs& a, cudaStream_t stream) {
+static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream) {
   if (a.W == 0) return MP_OK;
+  int rc = prepare_queue(h, a, a.W, stream);
+  if (rc) return rc;
   // small ensembles: 32-thread blocks spread the warps over more SMs
   if (a.W <= 148 * 64 * 4) {
     eval_kernel<MODE, 32><<<(a.W + 31) / 32, 32, 0, stream>>>(a);
+    eval_stiff_kernel<MODE, 32><<<stiff_grid(h, a.W, 32), 32, 0, stream>>>(a);
   } else {
     eval_kernel<MODE, 64><<<(a.W + 63) / 64, 64, 0, stream>>>(a);
+    eval_stiff_kernel<MODE, 64><<<stiff_grid(h, a.W, 64), 64, 0, stream>>>(a);
   }
   MP_CUDA(cudaGetLastError());
   return MP_OK;
@@ -436,7 +512,7 @@ extern "C" int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32
   a.lnp = d_lnp;
   a.status = d_status;
   a.n_rhs = d_n_rhs;
-  return launch_eval<kModeLnprob>(a, (cudaStream_t)stream);
+  return launch_eval<kModeLnprob>(h, a, (cudaStream_t)stream);
 }
 
 extern "C" int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int32_t ndim, double* lnp,
@@ -492,7 +568,7 @@ extern "C" int mp_model_at_data(mp_handle* h, const double* pars, int32_t W, int
   a.theta = h->s_theta;
   a.out = h->s_out;
   a.status = h->s_status;
-  if ((rc = launch_eval<kModeModelAtData>(a, h->stream))) return rc;
+  if ((rc = launch_eval<kModeModelAtData>(h, a, h->stream))) return rc;
   MP_CUDA(cudaMemcpyAsync(out, h->s_out, (size_t)W * h->D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (status) MP_CUDA(cudaMemcpyAsync(status, h->s_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   MP_CUDA(cudaStreamSynchronize(h->stream));
@@ -540,7 +616,7 @@ extern "C" int mp_model_curves_device(mp_handle* h, const double* d_pars, int32_
   a.out = d_out;
   a.state = d_state;
   a.status = d_status;
-  return launch_eval<kModeCurves>(a, (cudaStream_t)stream);
+  return launch_eval<kModeCurves>(h, a, (cudaStream_t)stream);
 }
 
 extern "C" int mp_model_curves(mp_handle* h, const double* pars, int32_t W, int32_t ndim, int32_t node_stride,
@@ -617,8 +693,14 @@ extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_ln
   s.step = step;
   s.accepted = d_accepted;
   if (n_active == 0) return MP_OK;
-  if (n_active <= 148 * 64 * 4) stretch_kernel<32><<<(n_active + 31) / 32, 32, 0, (cudaStream_t)stream>>>(s);
-  else stretch_kernel<64><<<(n_active + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s);
+  if ((rc = prepare_queue(h, s.k, n_active, (cudaStream_t)stream))) return rc;
+  if (n_active <= 148 * 64 * 4) {
+    stretch_kernel<32><<<(n_active + 31) / 32, 32, 0, (cudaStream_t)stream>>>(s);
+    stretch_stiff_kernel<32><<<stiff_grid(h, n_active, 32), 32, 0, (cudaStream_t)stream>>>(s);
+  } else {
+    stretch_kernel<64><<<(n_active + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s);
+    stretch_stiff_kernel<64><<<stiff_grid(h, n_active, 64), 64, 0, (cudaStream_t)stream>>>(s);
+  }
   MP_CUDA(cudaGetLastError());
   return MP_OK;
 }

@@ -45,7 +45,7 @@ extern "C" int hs_lnprob(const mp_model_spec* ms, const mp_prior_spec* pr, const
       unpack_theta(sp, th, ndim, pars, de, pe, fb);
       Walker wk;
       walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
-      double chi2 = evaluate_walker<kModeLnprob, 64>(sp, dv, wk, buf.data(), 1, st, nr, nullptr, nullptr, 1, nullptr);
+      double chi2 = evaluate_walker<kModeLnprob, 64, true>(sp, dv, wk, buf.data(), 1, st, nr, nullptr, nullptr, 1, nullptr);
       double ll = -0.5 * chi2;
       if (st & kWalkerIntegratorFail) ll = -INFINITY;
       else if (!std::isfinite(ll)) { st |= kWalkerNonfiniteLnlike; ll = -INFINITY; }
@@ -78,7 +78,7 @@ extern "C" int hs_curves(const mp_model_spec* ms, const double* grid, int G, con
     Walker wk;
     walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
     int st = 0, nr = 0;
-    evaluate_walker<kModeCurves, 64>(sp, dv, wk, buf.data(), 1, st, nr, out + (size_t)w * 3 * Gs,
+    evaluate_walker<kModeCurves, 64, true>(sp, dv, wk, buf.data(), 1, st, nr, out + (size_t)w * 3 * Gs,
                                      state ? state + (size_t)w * 2 * Gs : nullptr, 1, nullptr);
     if (status) status[w] = st;
     if (nrhs) nrhs[w] = nr;
@@ -117,9 +117,40 @@ extern "C" int hs_model_at(const mp_model_spec* ms, const double* grid, int G, c
     Walker wk;
     walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
     int st = 0, nr = 0;
-    evaluate_walker<kModeModelAtData, 64>(sp, dv, wk, buf.data(), 1, st, nr, out + (size_t)w * D, nullptr, 1,
+    evaluate_walker<kModeModelAtData, 64, true>(sp, dv, wk, buf.data(), 1, st, nr, out + (size_t)w * D, nullptr, 1,
                                           np.order.data());
     if (status) status[w] = st;
   }
   return 0;
+}
+
+// per-step trace of one walker (debug aid): rows of (t, h, omega, fastness-1, accepted, stiff, hJ)
+extern "C" int hs_trace(const mp_model_spec* ms, const double* grid, int G, const double* pars_in, double t_end,
+                        double* out, int max_rows) {
+  Spec sp = make_spec(*ms);
+  sp.unlog_mask = 0;
+  double pars[6], de, pe, fb;
+  unpack_theta(sp, pars_in, 6, pars, de, pe, fb);
+  Walker wk;
+  walker_setup(sp, pars, de, pe, fb, grid[0], wk);
+  Integrator in;
+  in.n_rhs = 0;
+  integrator_init(sp, wk, grid[0], t_end, in);
+  int n = 0;
+  while (in.t < t_end && in.status == 0 && n < max_rows) {
+    const double t0 = in.t, h0 = in.h;
+    const int stiff = in.stiff;
+    bool acc;
+    if (stiff) { const double tb = in.t; in = radau_step(sp, wk, t_end, in); acc = in.t > tb; }
+    else acc = integrator_step(sp, wk, t_end, in);
+    DiscAt d = disc_at(wk, in.t);
+    double f, J;
+    spin_rhs_jac(sp, wk, d, in.omega, f, J);
+    const bool cap = d.rm * in.omega >= wk.kc;
+    const double fast = cap ? wk.Ccap / sqrt(in.omega) : d.wq * in.omega;
+    double* r = out + (size_t)n * 8;
+    r[0] = t0; r[1] = h0; r[2] = in.omega; r[3] = fast - 1.0; r[4] = acc; r[5] = stiff; r[6] = h0 * J; r[7] = cap;
+    ++n;
+  }
+  return n;
 }
