@@ -345,7 +345,7 @@ def extras(args, liks, data, dev, rank, world, torch, O, A):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         return {"walkers": W, "ms": ms, "evals_per_s": W / ms * 1e3, "mean_rhs": float(d_n.double().mean().item()),
-                "max_rhs": int(d_n.max().item())}
+                "max_rhs": int(d_n.max().item()), "stiff_bucket": lk.last_stiff_count()}
 
     truth = O.SYNTH_TRUTHS_LOG[name]
     out["config2_exact_half_step_128_walkers"] = timed(truth + 1e-4 * rng.randn(128, 6), reps=20)

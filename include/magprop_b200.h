@@ -160,6 +160,10 @@ int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_lnp, int32_t 
                          double a, uint64_t seed, uint64_t step, int32_t* d_accepted,
                          int32_t* d_n_rhs, void* stream);
 
+/* Diagnostic: how many walkers of the most recent launch on this handle were bucketed as stiff
+ * and re-run by the implicit (Radau IIA) launch.  Synchronises the device.               */
+int mp_last_stiff_count(mp_handle* h, int32_t* count);
+
 /* FP64 FMA peak micro-benchmark (roofline denominator; MEASURED_PEAKS.json has
  * no FP64 entry): returns achieved TFLOP/s of dependent-chain-free DFMA.        */
 int mp_fp64_peak_tflops(int32_t device, double* tflops);

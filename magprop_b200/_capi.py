@@ -110,13 +110,14 @@ def declare(lib):
     lib.mp_stretch_half_step.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32,
                                          C.c_double, C.c_uint64, C.c_uint64, vp, vp, vp]
     lib.mp_fp64_peak_tflops.argtypes = [C.c_int32, _dp]
+    lib.mp_last_stiff_count.argtypes = [vp, _ip]
     return lib
 
 
 EXPORTS = ["mp_abi_version", "mp_device_count", "mp_last_error", "mp_create", "mp_destroy",
            "mp_set_prior", "mp_lnprob_batch", "mp_lnprob_batch_device", "mp_model_at_data",
            "mp_curve_nodes", "mp_model_curves", "mp_model_curves_device", "mp_rhs_batch",
-           "mp_stretch_half_step", "mp_fp64_peak_tflops"]
+           "mp_stretch_half_step", "mp_fp64_peak_tflops", "mp_last_stiff_count"]
 
 
 def load():

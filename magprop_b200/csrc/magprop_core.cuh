@@ -887,8 +887,17 @@ enum EvalMode { kModeLnprob = 0, kModeModelAtData = 1, kModeCurves = 2 };
 // not integrated implicitly here but returned with kWalkerDeferred, to be re-run by the
 // STIFF = true variant (the kernels bucket such walkers into a second launch, so the common
 // explicit path is compiled without the implicit integrator's register and stack footprint).
+// `live` = false makes the lane a bystander: it computes nothing but still takes part in the
+// warp votes of phase A.  Every lane of a warp must call this function (the kernels pass
+// live = false for lanes without a walker) -- see the note on convergence below.
+#if defined(__CUDA_ARCH__)
+#define MP_WARP_ANY(pred) __any_sync(0xffffffffu, (pred))
+#else
+#define MP_WARP_ANY(pred) (pred)
+#endif
+
 template <int MODE, int NB, bool STIFF>
-MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w, double* buf,
+MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w, bool live, double* buf,
                              int bstride, int& status, int& n_rhs, double* out,
                              double* state_out, int ostride, const int* dat_orig) {
   const int Nn = dv.n_nodes;
@@ -898,41 +907,53 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
   Integrator in;
   in.status = kWalkerOk;
   in.n_rhs = 0;
-  if (w.bad) {
-    status |= kWalkerNonfiniteState;
-  } else {
-    integrator_init(sp, w, dv.t_start, t_end, in);
-  }
+  in.stiff = 0;
+  in.t1 = dv.t_start;
+  const bool integrate = live && !w.bad;
+  if (live && w.bad) status |= kWalkerNonfiniteState;
+  if (integrate) integrator_init(sp, w, dv.t_start, t_end, in);
   int jn = 0, idat = 0;
   double chi2 = 0.0, Lprev = 0.0;
+  bool deferred = false;
   for (int c0 = 0; c0 < Nn; c0 += NB) {
     const int c1 = (c0 + NB < Nn) ? c0 + NB : Nn;
     // ---- phase A
-    if (w.bad) {
+    if (live && w.bad) {
       for (; jn < c1; ++jn)
         buf[(jn - c0) * bstride] = (ldg(dv.node_t + jn) == dv.t_start) ? w.omega0 : NAN;
-    } else {
-      while (jn < c1) {
-        const double tn = ldg(dv.node_t + jn);
-        if (tn <= in.t1) {
+    }
+    // Each trip: (1) drain every node the current dense segment covers -- cheap, divergent;
+    // (2) one integrator step for every lane that still needs one.  The vote between the two is
+    // what keeps the warp converged for the expensive part: without it the lanes that did / did
+    // not have a node to drain run the step one group after the other (measured 10x slower), and
+    // if a node cost a trip of its own the lanes would sit out each other's steps (measured: 197
+    // step bodies per warp for 142 steps per lane).
+    for (;;) {
+      bool step = false;
+      if (integrate && !deferred && jn < c1) {
+        while (jn < c1) {
+          const double tn = ldg(dv.node_t + jn);
+          if (!(tn <= in.t1)) break;
           buf[(jn - c0) * bstride] = dense_eval(in, tn);
           ++jn;
-        } else if (in.status != kWalkerOk) {
-          buf[(jn - c0) * bstride] = NAN;
-          ++jn;
-        } else if (in.stiff) {
-          if (STIFF) {
-            in = radau_step(sp, w, t_end, in);
+        }
+        if (jn < c1) {
+          if (in.status != kWalkerOk) {
+            for (; jn < c1; ++jn) buf[(jn - c0) * bstride] = NAN;
+          } else if (in.stiff && !STIFF) {
+            deferred = true;              // re-run by the stiff-capable launch
           } else {
-            status |= kWalkerDeferred;
-            n_rhs = in.n_rhs;
-            return 0.0;
+            step = true;
           }
-        } else {
-          integrator_step(sp, w, t_end, in);
         }
       }
+      if (!MP_WARP_ANY(step)) break;
+      if (step) {
+        if (STIFF && in.stiff) in = radau_step(sp, w, t_end, in);
+        else integrator_step(sp, w, t_end, in);
+      }
     }
+    if (!live || deferred) continue;
     // ---- phase B
     for (int j = c0; j < c1; ++j) {
       const double om = buf[(j - c0) * bstride];
@@ -975,6 +996,7 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
       }
     }
   }
+  if (deferred) status |= kWalkerDeferred;
   status |= in.status;
   n_rhs = in.n_rhs;
   return chi2;

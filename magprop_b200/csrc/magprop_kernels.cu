@@ -64,13 +64,16 @@ __device__ __forceinline__ void stage_theta(const double* __restrict__ theta, in
 #endif
 
 // One walker, end to end.  Returns true when the walker was deferred to the stiff launch.
+// `have` = false: this lane has no walker; it still walks through evaluate_walker as a bystander
+// because the warp votes there need every lane.
 template <int MODE, int BLOCK, bool STIFF>
-__device__ __forceinline__ bool eval_one(const KernelArgs& a, int w, const double* th, double* s_buf) {
+__device__ __forceinline__ bool eval_one(const KernelArgs& a, bool have, int w, const double* th, double* s_buf) {
   int st = kWalkerOk, nr = 0;
   double result = -INFINITY;
-  if (a.prior_enabled && !prior_accepts(th, a.ndim, a.lower, a.upper)) {
-    st = kWalkerPriorReject;                       // mcmc_eqns.py:66-69: model is skipped
-  } else {
+  const bool rejected = have && a.prior_enabled && !prior_accepts(th, a.ndim, a.lower, a.upper);
+  if (rejected) st = kWalkerPriorReject;           // mcmc_eqns.py:66-69: model is skipped
+  const bool live = have && !rejected;
+  {
     double pars[6], dipeff, propeff, f_beam;
     unpack_theta(a.sp, th, a.ndim, pars, dipeff, propeff, f_beam);
     Walker wk;
@@ -83,10 +86,10 @@ __device__ __forceinline__ bool eval_one(const KernelArgs& a, int w, const doubl
     } else if (MODE == kModeModelAtData) {
       out = a.out + (size_t)w * a.dv.n_data;
     }
-    const double chi2 = evaluate_walker<MODE, kNB, STIFF>(a.sp, a.dv, wk, s_buf + threadIdx.x, BLOCK, st, nr,
+    const double chi2 = evaluate_walker<MODE, kNB, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK, st, nr,
                                                           out, state, 1, a.dat_orig);
     if (!STIFF && (st & kWalkerDeferred)) return true;
-    if (MODE == kModeLnprob) {
+    if (live && MODE == kModeLnprob) {
       double ll = -0.5 * chi2;                     // mcmc_eqns.py:25
       if (st & kWalkerIntegratorFail) {
         ll = -INFINITY;                            // 'flag' -> -inf (mcmc_eqns.py:22-23)
@@ -97,6 +100,7 @@ __device__ __forceinline__ bool eval_one(const KernelArgs& a, int w, const doubl
       result = ll;                                 // + lnprior == 0.0
     }
   }
+  if (!have) return false;
   if (MODE == kModeLnprob) a.lnp[w] = result;
   if (a.status) a.status[w] = st;
   if (a.n_rhs) a.n_rhs[w] = nr;
@@ -111,8 +115,7 @@ eval_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
   stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta);
   const int w = blockIdx.x * BLOCK + threadIdx.x;
-  if (w >= a.W) return;
-  if (eval_one<MODE, BLOCK, false>(a, w, s_theta + threadIdx.x * a.ndim, s_buf))
+  if (eval_one<MODE, BLOCK, false>(a, w < a.W, w, s_theta + threadIdx.x * a.ndim, s_buf))
     a.queue[atomicAdd(a.queue_count, 1)] = w;
 }
 
@@ -121,11 +124,13 @@ template <int MODE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) eval_stiff_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ double s_buf[kNB * BLOCK];
   const int n = *a.queue_count;
-  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK) {
-    const int w = a.queue[i];
+  for (int base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {   // block-uniform trip count
+    const int i = base + threadIdx.x;
+    const bool have = i < n;
+    const int w = have ? a.queue[i] : 0;
     double th[MP_MAX_NDIM];
     for (int d = 0; d < a.ndim; ++d) th[d] = a.theta[(size_t)w * a.ndim + d];
-    eval_one<MODE, BLOCK, true>(a, w, th, s_buf);
+    eval_one<MODE, BLOCK, true>(a, have, w, th, s_buf);
   }
 }
 
@@ -172,7 +177,7 @@ struct StretchArgs {
 // fused with the likelihood so a half-step is one launch (plus the stiff-bucket launch, which
 // finds an empty queue for ensembles near the synthetic truths).  Returns true when deferred.
 template <int BLOCK, bool STIFF>
-__device__ __forceinline__ bool stretch_one(const StretchArgs& s, int me, double* s_buf) {
+__device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int me, double* s_buf) {
   const KernelArgs& a = s.k;
   const int ndim = a.ndim;
   // counter = (step, walker); two Philox blocks give u_z, u_partner, u_accept
@@ -196,18 +201,22 @@ __device__ __forceinline__ bool stretch_one(const StretchArgs& s, int me, double
   }
   int st = kWalkerOk, nr = 0;
   double lp_new = -INFINITY;
-  if (!a.prior_enabled || prior_accepts(q, ndim, a.lower, a.upper)) {
+  const bool live = have && (!a.prior_enabled || prior_accepts(q, ndim, a.lower, a.upper));
+  {
     double pars[6], dipeff, propeff, f_beam;
     unpack_theta(a.sp, q, ndim, pars, dipeff, propeff, f_beam);
     Walker wk;
     walker_setup(a.sp, pars, dipeff, propeff, f_beam, a.dv.t_start, wk);
-    const double chi2 = evaluate_walker<kModeLnprob, kNB, STIFF>(a.sp, a.dv, wk, s_buf + threadIdx.x, BLOCK, st,
-                                                                 nr, nullptr, nullptr, 1, nullptr);
+    const double chi2 = evaluate_walker<kModeLnprob, kNB, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK,
+                                                                 st, nr, nullptr, nullptr, 1, nullptr);
     if (!STIFF && (st & kWalkerDeferred)) return true;
-    double ll = -0.5 * chi2;
-    if ((st & kWalkerIntegratorFail) || !isfinite(ll)) ll = -INFINITY;
-    lp_new = ll;
+    if (live) {
+      double ll = -0.5 * chi2;
+      if ((st & kWalkerIntegratorFail) || !isfinite(ll)) ll = -INFINITY;
+      lp_new = ll;
+    }
   }
+  if (!have) return false;
   const double lp_old = s.lnp[me];
   const double lnpdiff = __dadd_rn(__dadd_rn(__dmul_rn(ndim - 1.0, log(z)), lp_new), -lp_old);
   if (lnpdiff > log(ua)) {
@@ -224,17 +233,20 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MI
 stretch_kernel(const __grid_constant__ StretchArgs s) {
   __shared__ double s_buf[kNB * BLOCK];
   const int i = blockIdx.x * BLOCK + threadIdx.x;
-  if (i >= s.n_active) return;
-  const int me = s.active[i];
-  if (stretch_one<BLOCK, false>(s, me, s_buf)) s.k.queue[atomicAdd(s.k.queue_count, 1)] = me;
+  const bool have = i < s.n_active;
+  const int me = have ? s.active[i] : s.active[0];
+  if (stretch_one<BLOCK, false>(s, have, me, s_buf)) s.k.queue[atomicAdd(s.k.queue_count, 1)] = me;
 }
 
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) stretch_stiff_kernel(const __grid_constant__ StretchArgs s) {
   __shared__ double s_buf[kNB * BLOCK];
   const int n = *s.k.queue_count;
-  for (int i = blockIdx.x * BLOCK + threadIdx.x; i < n; i += gridDim.x * BLOCK)
-    stretch_one<BLOCK, true>(s, s.k.queue[i], s_buf);
+  for (int base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
+    const int i = base + threadIdx.x;
+    const bool have = i < n;
+    stretch_one<BLOCK, true>(s, have, have ? s.k.queue[i] : s.active[0], s_buf);
+  }
 }
 
 // ---- the coupled right-hand side, as ODEs()/odes() return it -----------------------
@@ -702,6 +714,14 @@ extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_ln
     stretch_stiff_kernel<64><<<stiff_grid(h, n_active, 64), 64, 0, (cudaStream_t)stream>>>(s);
   }
   MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
+extern "C" int mp_last_stiff_count(mp_handle* h, int32_t* count) {
+  if (!h || !count) return fail(MP_ERR_BAD_ARG, "mp_last_stiff_count: null pointer");
+  MP_CUDA(cudaSetDevice(h->device));
+  MP_CUDA(cudaDeviceSynchronize());
+  MP_CUDA(cudaMemcpy(count, h->d_queue_count, sizeof(int), cudaMemcpyDeviceToHost));
   return MP_OK;
 }
 

@@ -127,6 +127,12 @@ class Likelihood:
             idx.append(self.grid.size - 1)
         return self.grid[idx]
 
+    def last_stiff_count(self) -> int:
+        """Walkers of the last launch that were bucketed as stiff (synchronises)."""
+        n = C.c_int32(0)
+        A.check(self._lib.mp_last_stiff_count(self._h, C.byref(n)))
+        return n.value
+
     def stretch_half_step(self, d_coords, d_lnp, nwalkers, ndim, d_active, n_active, d_complement,
                           n_complement, a, seed, step, d_accepted=0, d_nrhs=0, stream=0):
         A.check(self._lib.mp_stretch_half_step(self._h, d_coords, d_lnp, nwalkers, ndim, d_active, n_active,
