@@ -899,7 +899,7 @@ enum EvalMode { kModeLnprob = 0, kModeModelAtData = 1, kModeCurves = 2 };
 template <int MODE, int NB, bool STIFF>
 MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w, bool live, double* buf,
                              int bstride, int& status, int& n_rhs, double* out,
-                             double* state_out, int ostride, const int* dat_orig) {
+                             double* state_out, int ostride, const int* dat_orig, void* warp_scratch) {
   const int Nn = dv.n_nodes;
   n_rhs = 0;
   if (Nn <= 0) return 0.0;
@@ -953,6 +953,42 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
         else integrator_step(sp, w, t_end, in);
       }
     }
+#if defined(__CUDA_ARCH__)
+    if (MODE == kModeCurves) {
+      // ---- phase B, curve output: transposed.  The warp takes its 32 walkers one at a time and
+      // evaluates that walker's luminosity stage with one NODE per lane, so the three output rows
+      // (and the state rows) are written as 256-byte runs along the node axis instead of 8-byte
+      // writes 3*Gs*8 bytes apart.  Same work as the lane-per-walker form, coalesced stores.
+      const unsigned FULL = 0xffffffffu;
+      const int lane = threadIdx.x & 31;
+      Walker* sw = static_cast<Walker*>(warp_scratch);
+      unsigned srcmask = __ballot_sync(FULL, live && !deferred);
+      while (srcmask) {
+        const int src = __ffs(srcmask) - 1;
+        srcmask &= srcmask - 1;
+        if (lane == src) *sw = w;
+        double* o = reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(out), src));
+        double* so = reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(state_out), src));
+        __syncwarp();
+        const int j = c0 + lane;
+        if (j < c1) {
+          const double tn = ldg(dv.node_t + j);
+          const double om = buf[lane * bstride + (src - lane)];        // column of lane `src`, row `lane`
+          const double M = sw->bad ? ((tn == dv.t_start) ? sw->M_init : NAN) : disc_mass(*sw, tn);
+          const Lum L = luminosity(sp, *sw, M, om);
+          o[j] = L.tot / 1.0e50;
+          o[Nn + j] = L.prop / 1.0e50;
+          o[2 * Nn + j] = L.dip / 1.0e50;
+          if (so) {
+            so[j] = M;
+            so[Nn + j] = om;
+          }
+        }
+        __syncwarp();
+      }
+      continue;
+    }
+#endif
     if (!live || deferred) continue;
     // ---- phase B
     for (int j = c0; j < c1; ++j) {

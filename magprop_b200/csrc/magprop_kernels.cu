@@ -67,7 +67,7 @@ __device__ __forceinline__ void stage_theta(const double* __restrict__ theta, in
 // `have` = false: this lane has no walker; it still walks through evaluate_walker as a bystander
 // because the warp votes there need every lane.
 template <int MODE, int BLOCK, bool STIFF>
-__device__ __forceinline__ bool eval_one(const KernelArgs& a, bool have, int w, const double* th, double* s_buf) {
+__device__ __forceinline__ bool eval_one(const KernelArgs& a, bool have, int w, const double* th, double* s_buf, void* warp_scratch) {
   int st = kWalkerOk, nr = 0;
   double result = -INFINITY;
   const bool rejected = have && a.prior_enabled && !prior_accepts(th, a.ndim, a.lower, a.upper);
@@ -87,7 +87,7 @@ __device__ __forceinline__ bool eval_one(const KernelArgs& a, bool have, int w, 
       out = a.out + (size_t)w * a.dv.n_data;
     }
     const double chi2 = evaluate_walker<MODE, kNB, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK, st, nr,
-                                                          out, state, 1, a.dat_orig);
+                                                          out, state, 1, a.dat_orig, warp_scratch);
     if (!STIFF && (st & kWalkerDeferred)) return true;
     if (live && MODE == kModeLnprob) {
       double ll = -0.5 * chi2;                     // mcmc_eqns.py:25
@@ -113,9 +113,11 @@ __global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MI
 eval_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ double s_buf[kNB * BLOCK];
   __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
+  __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];   // per-warp broadcast slot (curve output)
   stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta);
   const int w = blockIdx.x * BLOCK + threadIdx.x;
-  if (eval_one<MODE, BLOCK, false>(a, w < a.W, w, s_theta + threadIdx.x * a.ndim, s_buf))
+  void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
+  if (eval_one<MODE, BLOCK, false>(a, w < a.W, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch))
     a.queue[atomicAdd(a.queue_count, 1)] = w;
 }
 
@@ -123,6 +125,8 @@ eval_kernel(const __grid_constant__ KernelArgs a) {
 template <int MODE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) eval_stiff_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ double s_buf[kNB * BLOCK];
+  __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];
+  void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
   const int n = *a.queue_count;
   for (int base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {   // block-uniform trip count
     const int i = base + threadIdx.x;
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(BLOCK) eval_stiff_kernel(const __grid_constant
     const int w = have ? a.queue[i] : 0;
     double th[MP_MAX_NDIM];
     for (int d = 0; d < a.ndim; ++d) th[d] = a.theta[(size_t)w * a.ndim + d];
-    eval_one<MODE, BLOCK, true>(a, have, w, th, s_buf);
+    eval_one<MODE, BLOCK, true>(a, have, w, th, s_buf, scratch);
   }
 }
 
@@ -208,7 +212,7 @@ __device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int
     Walker wk;
     walker_setup(a.sp, pars, dipeff, propeff, f_beam, a.dv.t_start, wk);
     const double chi2 = evaluate_walker<kModeLnprob, kNB, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK,
-                                                                 st, nr, nullptr, nullptr, 1, nullptr);
+                                                                 st, nr, nullptr, nullptr, 1, nullptr, nullptr);
     if (!STIFF && (st & kWalkerDeferred)) return true;
     if (live) {
       double ll = -0.5 * chi2;

@@ -45,7 +45,7 @@ extern "C" int hs_lnprob(const mp_model_spec* ms, const mp_prior_spec* pr, const
       unpack_theta(sp, th, ndim, pars, de, pe, fb);
       Walker wk;
       walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
-      double chi2 = evaluate_walker<kModeLnprob, 64, true>(sp, dv, wk, true, buf.data(), 1, st, nr, nullptr, nullptr, 1, nullptr);
+      double chi2 = evaluate_walker<kModeLnprob, 64, true>(sp, dv, wk, true, buf.data(), 1, st, nr, nullptr, nullptr, 1, nullptr, nullptr);
       double ll = -0.5 * chi2;
       if (st & kWalkerIntegratorFail) ll = -INFINITY;
       else if (!std::isfinite(ll)) { st |= kWalkerNonfiniteLnlike; ll = -INFINITY; }
@@ -79,7 +79,7 @@ extern "C" int hs_curves(const mp_model_spec* ms, const double* grid, int G, con
     walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
     int st = 0, nr = 0;
     evaluate_walker<kModeCurves, 64, true>(sp, dv, wk, true, buf.data(), 1, st, nr, out + (size_t)w * 3 * Gs,
-                                     state ? state + (size_t)w * 2 * Gs : nullptr, 1, nullptr);
+                                     state ? state + (size_t)w * 2 * Gs : nullptr, 1, nullptr, nullptr);
     if (status) status[w] = st;
     if (nrhs) nrhs[w] = nr;
   }
@@ -118,7 +118,7 @@ extern "C" int hs_model_at(const mp_model_spec* ms, const double* grid, int G, c
     walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
     int st = 0, nr = 0;
     evaluate_walker<kModeModelAtData, 64, true>(sp, dv, wk, true, buf.data(), 1, st, nr, out + (size_t)w * D, nullptr, 1,
-                                          np.order.data());
+                                          np.order.data(), nullptr);
     if (status) status[w] = st;
   }
   return 0;
