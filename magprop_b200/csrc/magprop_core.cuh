@@ -28,14 +28,14 @@
 
 #if defined(__CUDACC__)
 #define MP_HD __host__ __device__ __forceinline__
-#define MP_TABLE_QUALIFIER __device__ const
+#define MP_TABLE_QUALIFIER __device__ const __align__(16)
 // NOT const on the device: a const __constant__ array with a visible initialiser is folded into
 // immediates, and every FP64 immediate costs two extra MOVs; a mutable one stays a c[3][..] operand.
 #define MP_CONST_QUALIFIER __constant__
 #else
 #define MP_CONST_QUALIFIER static const
 #define MP_HD inline
-#define MP_TABLE_QUALIFIER static const
+#define MP_TABLE_QUALIFIER alignas(16) static const
 #endif
 
 #include "disc_table.inc"
@@ -69,6 +69,10 @@ struct Spec {
   double omega2_breakup_rhs;   // omega^2 above which rot_param > breakup_rhs
   double omega2_breakup_lum;
   double sqrt_GMR;             // sqrt(GM*R): lever arm when Rm < R
+  double kc;                   // rhs_k * c : capped when Rm*omega >= kc
+  double Ccap;                 // kc^(3/2)/sqrt(GM): capped fastness = Ccap / sqrt(omega)
+  double sGMkc;                // sqrt(GM*kc): capped lever = sGMkc / sqrt(omega)
+  double sqrtGM, inv_sqrtGM;
   int lprop_binding_term;
   int unlog_mask;
   double rtol;
@@ -151,6 +155,49 @@ MP_HD double poly10(const double* c, double s) {
   return fma(od, s, ev);
 }
 
+// Two adjacent table coefficients in one 16-byte load (rows are 16-byte aligned).
+struct alignas(16) Pair { double x, y; };
+MP_HD Pair ld2(const double* p) {
+#if defined(__CUDA_ARCH__)
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  Pair r; r.x = v.x; r.y = v.y; return r;
+#else
+  Pair r; r.x = p[0]; r.y = p[1]; return r;
+#endif
+}
+
+// poly10 with paired loads: (c0,c1) (c2,c3) ... (c10,pad) feed the even and the odd chain.
+MP_HD double poly10p(const double* c, double s, double s2) {
+  const Pair p5 = ld2(c + 10), p4 = ld2(c + 8), p3 = ld2(c + 6), p2 = ld2(c + 4), p1 = ld2(c + 2), p0 = ld2(c);
+  double ev = p5.x, od = p4.y;
+  ev = fma(ev, s2, p4.x);
+  od = fma(od, s2, p3.y);
+  ev = fma(ev, s2, p3.x);
+  od = fma(od, s2, p2.y);
+  ev = fma(ev, s2, p2.x);
+  od = fma(od, s2, p1.y);
+  ev = fma(ev, s2, p1.x);
+  od = fma(od, s2, p0.y);
+  ev = fma(ev, s2, p0.x);
+  return fma(od, s, ev);
+}
+
+// table_locate that always yields a loadable row (row 0 when u is outside the table), so the
+// caller can evaluate unconditionally and patch the rare outside case afterwards.
+MP_HD bool table_locate_safe(double u, TableAt& ta) {
+  const int64_t b = dbits(u);
+  const int e = (int)((b >> 52) & 0x7ff) - 1023;
+  ta.e = e;
+  const bool in = (b > 0) && ((unsigned)(e - MP_DISC_EMIN) <= (unsigned)(MP_DISC_EMAX - MP_DISC_EMIN));
+  const int sub = (int)((b >> (52 - MP_DISC_NSUB_LOG2)) & ((1 << MP_DISC_NSUB_LOG2) - 1));
+  const int idx = in ? (((e - MP_DISC_EMIN) << MP_DISC_NSUB_LOG2) + sub) : 0;
+  ta.row = &mp_disc_table[idx][0];
+  const double m = bitsd((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+  const double centre = 1.0 + (sub + 0.5) * (1.0 / (1 << MP_DISC_NSUB_LOG2));
+  ta.s = (m - centre) * (double)(2 << MP_DISC_NSUB_LOG2);
+  return in;
+}
+
 // S outside the table (rare): convergent series below 2^-10, asymptotic above 2^22.
 // Kept out of line so the hot stage loop stays small.
 #if defined(__CUDACC__)
@@ -194,6 +241,11 @@ struct Walker {
   double sGMA;     // sqrt(GM*A_rm): lever(uncapped) = sGMA * M^(-1/7)
   double sGMkc;    // sqrt(GM*k*c):  lever(capped)   = sGMkc / sqrt(omega)
   double Cdip_I;   // mu^2/(6c^3)/I
+  // folded forms used by the explicit step (spin_f): with qa = sqrtA * M^(-1/7),
+  //   Rm = qa^2,  w/omega = qa^3/sqrt(GM),  lever = sqrt(GM) qa,  N_acc/I = -lever * ni * tanh
+  double sqrtA;    // sqrt(A_rm)
+  double KqA;      // Kq * sqrtA : late-phase qa = KqA * Q(u)
+  double tvI;      // 1/(tvisc I) : ni = Mdisc * tvI
   // luminosity stage (its own alpha/cs7/k/n may differ from the RHS's)
   double l_inv_tv, l_A_rm, l_Cw, l_Ccap, l_kc;
   double Ldip_coef;   // mu^2/(6 c^3)
@@ -333,6 +385,9 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
   w.kc = sp.rhs_k * kC;
   w.Ccap = w.kc * sqrt(w.kc) / sqrt(kGM);
   w.sGMA = sqrt(kGM * w.A_rm);
+  w.sqrtA = sqrt(w.A_rm);
+  w.KqA = w.Kq * w.sqrtA;
+  w.tvI = w.inv_tv * sp.inv_inertia;
   w.sGMkc = sqrt(kGM * w.kc);
   w.Ldip_coef = (mu * mu) / (6.0 * (kC * kC * kC));
   w.Cdip_I = w.Ldip_coef * sp.inv_inertia;
@@ -511,6 +566,85 @@ MP_HD Lum luminosity(const Spec& sp, const Walker& w, double M, double omega) {
   return L;
 }
 
+// ---- branch-free forms for the explicit step ------------------------------------------
+// The step below evaluates the five disc-mass stages of a step as one block and then the six
+// spin-equation stages as one serial chain; both blocks are straight-line code (selects, no
+// branches) so the compiler can overlap the independent chains.  CUDA's rsqrt()/division carry a
+// special-case branch each; the arguments here are positive and normal, so the Newton forms are
+// used bare.
+MP_HD double rsqrt_pos(double x) {      // x > 0, normal
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));     // ~2^-22
+  const double e = fma(x, -(r * r), 1.0);
+  return fma(fma(e, 0.375, 0.5), r * e, r);                    // third order: ~2^-64
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
+MP_HD double rcp_pos(double x) {        // 1 <= x (0 for x = inf or beyond 2^1022)
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));       // ~2^-22
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  return fma(r, e, r);                                         // e^3: ~2^-64
+#else
+  return 1.0 / x;
+#endif
+}
+
+// exp(x) for the tanh below: argument clamped to [-80, 80] (beyond that tanh is +-1 to the last
+// bit), NaN propagates.
+MP_HD double exp_tanh_arg(double x) {
+  double xc = (x < -80.0) ? -80.0 : x;
+  xc = (xc > 80.0) ? 80.0 : xc;
+  const double kd = fma(xc, kExpR[0], kExpR[1]);
+  const int k = (int)(dbits(kd) & 0xffffffffLL);
+  const double kf = kd - kExpR[1];
+  double r = fma(kf, kExpR[2], xc);
+  r = fma(kf, kExpR[3], r);
+  const double r2 = r * r;
+  double ev = kExpC[12], od = kExpC[11];
+  ev = fma(ev, r2, kExpC[10]);
+  od = fma(od, r2, kExpC[9]);
+  ev = fma(ev, r2, kExpC[8]);
+  od = fma(od, r2, kExpC[7]);
+  ev = fma(ev, r2, kExpC[6]);
+  od = fma(od, r2, kExpC[5]);
+  ev = fma(ev, r2, kExpC[4]);
+  od = fma(od, r2, kExpC[3]);
+  ev = fma(ev, r2, kExpC[2]);
+  od = fma(od, r2, kExpC[1]);
+  ev = fma(ev, r2, kExpC[0]);
+  const double p = fma(od, r, ev);
+  const double res = bitsd(dbits(p) + ((int64_t)k << 52));
+  return (x == x) ? res : x;
+}
+
+// Disc quantities of one Runge-Kutta stage, in the folded form spin_f wants.
+struct StageDisc {
+  double qa;   // sqrt(A_rm) * Mdisc^(-1/7)
+  double ni;   // Mdisc / (tvisc I)
+};
+
+// d(omega)/dt, same mathematics as spin_rhs (funcs.py:105-140), branch-free.
+MP_HD double spin_f(const Spec& sp, const Walker& w, const StageDisc& d, double omega) {
+  const double rm = d.qa * d.qa;                               // uncapped Alfven radius
+  const double r = rsqrt_pos(omega);
+  const bool capped = rm * omega >= sp.kc;                     // Rm >= k*Rlc (funcs.py:109-110)
+  const double fast_u = (rm * d.qa) * (sp.inv_sqrtGM * omega);
+  const double fast = capped ? sp.Ccap * r : fast_u;
+  const double lev_u = (rm >= kR) ? sp.sqrtGM * d.qa : sp.sqrt_GMR;            // funcs.py:135-138
+  const double lev_c = (sp.kc >= kR * omega) ? sp.sGMkc * r : sp.sqrt_GMR;
+  const double lever = capped ? lev_c : lev_u;
+  const double om2 = omega * omega;
+  const double e2 = exp_tanh_arg(2.0 * (sp.rhs_n * (fast - 1.0)));
+  double th = fma(-2.0, rcp_pos(e2 + 1.0), 1.0);               // tanh(n (w - 1))
+  th = (om2 > sp.omega2_breakup_rhs) ? 0.0 : th;               // funcs.py:131-132
+  return fma(-w.Cdip_I * om2, omega, -(lever * d.ni) * th);
+}
+
 // ---- Dormand-Prince 5(4) with dense output --------------------------------
 // Coefficients: Dormand & Prince 1980; dense output: Hairer, Norsett & Wanner II.6.
 // "Push" form: once k_j is known it is added straight into the running sums of the
@@ -604,8 +738,9 @@ MP_HD void controller(float err, float facold, float& fac11, float& fac) {
 }
 
 // Attempt one step; on acceptance advances (t, omega) and refreshes the dense
-// output.  Returns true when a step was accepted.
-MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
+// output.  Returns true when a step was accepted.  (Rolled push-form variant: one inlined copy of
+// disc_at + f in a 5-trip loop; kept for A/B measurements, -DMP_STEP_ROLLED.)
+MP_HD bool integrator_step_rolled(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
   const double t = in.t, y = in.omega;
   double h = in.h;
   bool last = false;
@@ -680,6 +815,149 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
     // estimate grows before the stability limit 3.3 is reached), i.e. at steps far smaller than
     // the time scale t on which the solution itself varies.  12 such steps in a row hand the
     // walker to the implicit integrator.
+#ifndef MP_NO_VOTES
+    const double dy = fabs(ynew - y6);
+    if (fabs(k7 - k6) * tn > 30.0 * dy && h < 0.02 * tn) {   // |lambda| t > 30 while h << t
+      if (++in.stiff_votes >= 12) { in.stiff = 1; in.stiff_votes = 0; }
+    } else {
+      in.stiff_votes = 0;
+    }
+#endif
+    return true;
+  }
+  // rejected
+  const double hnew = h / (double)fminf(facc1, fac11 / safe);
+  in.h = hnew;
+  in.rejected = 1;
+  in.n_steps++;
+  if (!(fabs(hnew) > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
+  return false;
+}
+
+// Dormand-Prince tableau (classic form) for the block step.
+struct DP {
+  static constexpr double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
+  static constexpr double a21 = 1.0 / 5;
+  static constexpr double a31 = 3.0 / 40, a32 = 9.0 / 40;
+  static constexpr double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
+  static constexpr double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
+  static constexpr double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656;
+  static constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+  static constexpr double e1 = 71.0 / 57600, e3 = -71.0 / 16695, e4 = 71.0 / 1920, e5 = -17253.0 / 339200, e6 = 22.0 / 525, e7 = -1.0 / 40;
+  static constexpr double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0,
+                          d4 = -10690763975.0 / 1880347072.0, d5 = 701980252875.0 / 199316789632.0,
+                          d6 = -1453857185.0 / 822651844.0, d7 = 69997945.0 / 29380423.0;
+};
+
+// Block form of the step (the default).  A step's five new stage times depend on (t, h) only, so
+// the disc-mass work of all five stages -- ten degree-10 polynomials in the late phase; five
+// polynomials, exponentials and x^(-1/7) before it -- is evaluated first as one block of
+// independent chains (that is where the FP64 pipe gets saturated); the six evaluations of the
+// scalar spin equation, which are inherently serial, follow as one straight-line chain.
+MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
+  const double t = in.t, y = in.omega;
+  double h = in.h;
+  bool last = false;
+  if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
+  const double tn = last ? t_end : t + h;
+  const double ts[5] = {fma(DP::c2, h, t), fma(DP::c3, h, t), fma(DP::c4, h, t), fma(DP::c5, h, t), tn};
+  // ---- disc block
+  double u[5];
+  TableAt ta[5];
+  bool in_all = true;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    u[s] = fma(ts[s], w.inv_tv, w.eps);
+    in_all = table_locate_safe(u[s], ta[s]) && in_all;
+  }
+  StageDisc d[5];
+  if (in_all && u[0] >= w.u_late) {
+    // late phase: S and Q = S^(-1/7) from the same table row -- no exp, no log
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const double s2 = ta[s].s * ta[s].s;
+      const double S = poly10p(ta[s].row, ta[s].s, s2);
+      const double Q = poly10p(ta[s].row + MP_DISC_ROW, ta[s].s, s2);
+      d[s].ni = (w.K * S) * w.tvI;
+      d[s].qa = w.KqA * Q;
+    }
+  } else {
+    double S[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s) S[s] = poly10p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
+    if (!in_all) {                                      // parameters far outside the prior box
+#pragma unroll
+      for (int s = 0; s < 5; ++s) {
+        TableAt tb;
+        if (!table_locate(u[s], tb)) S[s] = disc_S_outside(u[s], tb.e);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const double E = exp_c(w.u0 - u[s]);
+      const double M = fma(w.K, S[s], w.C * E);
+      d[s].ni = M * w.tvI;
+      d[s].qa = w.sqrtA * pow_m17_fast(M);
+    }
+  }
+  // ---- spin chain
+  const double k1 = in.k1;
+  const double y2 = fma(h, DP::a21 * k1, y);
+  const double k2 = spin_f(sp, w, d[0], y2);
+  const double y3 = fma(h, fma(DP::a32, k2, DP::a31 * k1), y);
+  const double k3 = spin_f(sp, w, d[1], y3);
+  const double y4 = fma(h, fma(DP::a43, k3, fma(DP::a42, k2, DP::a41 * k1)), y);
+  const double k4 = spin_f(sp, w, d[2], y4);
+  const double y5 = fma(h, fma(DP::a54, k4, fma(DP::a53, k3, fma(DP::a52, k2, DP::a51 * k1))), y);
+  const double k5 = spin_f(sp, w, d[3], y5);
+  const double y6 = fma(h, fma(DP::a65, k5, fma(DP::a64, k4, fma(DP::a63, k3, fma(DP::a62, k2, DP::a61 * k1)))), y);
+  const double k6 = spin_f(sp, w, d[4], y6);
+  const double ynew = fma(h, fma(DP::b6, k6, fma(DP::b5, k5, fma(DP::b4, k4, fma(DP::b3, k3, DP::b1 * k1)))), y);
+  const double k7 = spin_f(sp, w, d[4], ynew);
+  in.n_rhs += 6;
+  const double esum = fma(DP::e7, k7, fma(DP::e6, k6, fma(DP::e5, k5, fma(DP::e4, k4, fma(DP::e3, k3, DP::e1 * k1)))));
+  const double errv = h * esum;
+  const double sk = sp.rtol * fmax(fabs(y), fabs(ynew));
+  const double aerr = fabs(errv);
+  const bool accept = aerr <= sk;                 // false for NaN
+  float errf = (float)aerr / (float)sk;
+  if (!(errf == errf)) errf = 1.0e10f;            // NaN => shrink hard
+  float fac11, fac;
+  controller(errf, in.facold, fac11, fac);
+  const float safe = 0.9f, facc1 = 5.0f, facc2 = 0.1f;   // h may shrink 5x, grow 10x
+  if (accept) {
+    fac = fmaxf(facc2, fminf(facc1, fac / safe));
+    const double hnew = h / (double)fac;
+    in.facold = fmaxf(errf, 1.0e-4f);
+    // dense output (Hairer's contd5)
+    const double dsum = fma(DP::d7, k7, fma(DP::d6, k6, fma(DP::d5, k5, fma(DP::d4, k4, fma(DP::d3, k3, DP::d1 * k1)))));
+    const double ydiff = ynew - y;
+    const double bspl = fma(h, k1, -ydiff);
+    in.r1 = y;
+    in.r2 = ydiff;
+    in.r3 = bspl;
+    in.r4 = ydiff - h * k7 - bspl;
+    in.r5 = h * dsum;
+    in.t0 = t; in.hs = h; in.t1 = tn;
+    in.t = tn;
+    in.omega = ynew;
+    in.k1 = k7;
+#ifndef MP_NO_SLIDING
+    {
+      // break-up sliding mode (see breakup_sliding): crossing the boundary while the accretion
+      // torque just inside it still outweighs the dipole torque
+      const bool above_old = y * y > sp.omega2_breakup_rhs;
+      const bool above_new = ynew * ynew > sp.omega2_breakup_rhs;
+      if (above_old != above_new) {
+        const double om_c = sqrt(sp.omega2_breakup_rhs) * (1.0 - 1.0e-12);
+        if (spin_f(sp, w, d[4], om_c) > 0.0) in.status = kWalkerIntegratorFail;
+      }
+    }
+#endif
+    in.h = in.rejected ? fmin(hnew, h) : hnew;
+    in.rejected = 0;
+    in.n_steps++;
+    // stiffness detection: see integrator_step_rolled
 #ifndef MP_NO_VOTES
     const double dy = fabs(ynew - y6);
     if (fabs(k7 - k6) * tn > 30.0 * dy && h < 0.02 * tn) {   // |lambda| t > 30 while h << t
@@ -950,7 +1228,11 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
       if (!MP_WARP_ANY(step)) break;
       if (step) {
         if (STIFF && in.stiff) in = radau_step(sp, w, t_end, in);
+#if defined(MP_STEP_ROLLED)
+        else integrator_step_rolled(sp, w, t_end, in);
+#else
         else integrator_step(sp, w, t_end, in);
+#endif
       }
     }
 #if defined(__CUDA_ARCH__)

@@ -33,6 +33,11 @@ inline Spec make_spec(const mp_model_spec& m) {
   s.omega2_breakup_rhs = m.breakup_rhs * modW / (0.5 * s.inertia);
   s.omega2_breakup_lum = m.breakup_lum * modW / (0.5 * s.inertia);
   s.sqrt_GMR = std::sqrt(kGM * kR);
+  s.kc = m.rhs_k * kC;
+  s.Ccap = s.kc * std::sqrt(s.kc) / std::sqrt(kGM);
+  s.sGMkc = std::sqrt(kGM * s.kc);
+  s.sqrtGM = std::sqrt(kGM);
+  s.inv_sqrtGM = 1.0 / s.sqrtGM;
   s.lprop_binding_term = m.lprop_binding_term;
   s.unlog_mask = m.unlog_mask;
   s.rtol = (m.rtol > 0.0) ? m.rtol : 1.0e-10;
