@@ -594,15 +594,12 @@ MP_HD double rcp_pos(double x) {        // 1 <= x (0 for x = inf or beyond 2^102
 #endif
 }
 
-// exp(x) for the tanh below: argument clamped to [-80, 80] (beyond that tanh is +-1 to the last
-// bit), NaN propagates.
-MP_HD double exp_tanh_arg(double x) {
-  double xc = (x < -80.0) ? -80.0 : x;
-  xc = (xc > 80.0) ? 80.0 : xc;
-  const double kd = fma(xc, kExpR[0], kExpR[1]);
+// exp(x) for |x| <= 40 (no clamping, no NaN handling: the caller guards both).
+MP_HD double exp_small(double x) {
+  const double kd = fma(x, kExpR[0], kExpR[1]);
   const int k = (int)(dbits(kd) & 0xffffffffLL);
   const double kf = kd - kExpR[1];
-  double r = fma(kf, kExpR[2], xc);
+  double r = fma(kf, kExpR[2], x);
   r = fma(kf, kExpR[3], r);
   const double r2 = r * r;
   double ev = kExpC[12], od = kExpC[11];
@@ -618,8 +615,7 @@ MP_HD double exp_tanh_arg(double x) {
   od = fma(od, r2, kExpC[1]);
   ev = fma(ev, r2, kExpC[0]);
   const double p = fma(od, r, ev);
-  const double res = bitsd(dbits(p) + ((int64_t)k << 52));
-  return (x == x) ? res : x;
+  return bitsd(dbits(p) + ((int64_t)k << 52));
 }
 
 // Disc quantities of one Runge-Kutta stage, in the folded form spin_f wants.
@@ -635,12 +631,18 @@ MP_HD double spin_f(const Spec& sp, const Walker& w, const StageDisc& d, double 
   const bool capped = rm * omega >= sp.kc;                     // Rm >= k*Rlc (funcs.py:109-110)
   const double fast_u = (rm * d.qa) * (sp.inv_sqrtGM * omega);
   const double fast = capped ? sp.Ccap * r : fast_u;
-  const double lev_u = (rm >= kR) ? sp.sqrtGM * d.qa : sp.sqrt_GMR;            // funcs.py:135-138
+  // (a NaN qa must reach the result: the selects below keep the NaN operand when a comparison fails)
+  const double lev_u = (rm < kR) ? sp.sqrt_GMR : sp.sqrtGM * d.qa;            // funcs.py:135-138
   const double lev_c = (sp.kc >= kR * omega) ? sp.sGMkc * r : sp.sqrt_GMR;
   const double lever = capped ? lev_c : lev_u;
   const double om2 = omega * omega;
-  const double e2 = exp_tanh_arg(2.0 * (sp.rhs_n * (fast - 1.0)));
-  double th = fma(-2.0, rcp_pos(e2 + 1.0), 1.0);               // tanh(n (w - 1))
+  // tanh(n (w - 1)) to 4e-16 absolute; beyond |x| = 19.1 it is +-1 to the last bit (most stages of a
+  // propeller-phase walker), so the exponential is skipped there
+  const double x = sp.rhs_n * (fast - 1.0);
+  double th;
+  if (x > 19.1) th = 1.0;
+  else if (x < -19.1) th = -1.0;
+  else th = fma(-2.0, rcp_pos(exp_small(x + x) + 1.0), 1.0);
   th = (om2 > sp.omega2_breakup_rhs) ? 0.0 : th;               // funcs.py:131-132
   return fma(-w.Cdip_I * om2, omega, -(lever * d.ni) * th);
 }
@@ -834,19 +836,27 @@ MP_HD bool integrator_step_rolled(const Spec& sp, const Walker& w, double t_end,
   return false;
 }
 
-// Dormand-Prince tableau (classic form) for the block step.
+// Dormand-Prince tableau (classic form) for the block step, as constant-bank operands.
+MP_CONST_QUALIFIER double kDP[36] = {
+    1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9,                                                   // 0: c2..c5
+    1.0 / 5,                                                                               // 4: a21
+    3.0 / 40, 9.0 / 40,                                                                    // 5: a31 a32
+    44.0 / 45, -56.0 / 15, 32.0 / 9,                                                       // 7: a41..a43
+    19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729,                         // 10: a51..a54
+    9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656,               // 14: a61..a65
+    35.0 / 384, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84,                      // 19: b1 b3 b4 b5 b6
+    71.0 / 57600, -71.0 / 16695, 71.0 / 1920, -17253.0 / 339200, 22.0 / 525, -1.0 / 40,    // 24: e1 e3 e4 e5 e6 e7
+    -12715105075.0 / 11282082432.0, 87487479700.0 / 32700410799.0, -10690763975.0 / 1880347072.0,
+    701980252875.0 / 199316789632.0, -1453857185.0 / 822651844.0, 69997945.0 / 29380423.0};  // 30: d1 d3 d4 d5 d6 d7
+#define MP_DPK(name, idx) static MP_HD double name() { return kDP[idx]; }
 struct DP {
-  static constexpr double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
-  static constexpr double a21 = 1.0 / 5;
-  static constexpr double a31 = 3.0 / 40, a32 = 9.0 / 40;
-  static constexpr double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
-  static constexpr double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
-  static constexpr double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176, a65 = -5103.0 / 18656;
-  static constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
-  static constexpr double e1 = 71.0 / 57600, e3 = -71.0 / 16695, e4 = 71.0 / 1920, e5 = -17253.0 / 339200, e6 = 22.0 / 525, e7 = -1.0 / 40;
-  static constexpr double d1 = -12715105075.0 / 11282082432.0, d3 = 87487479700.0 / 32700410799.0,
-                          d4 = -10690763975.0 / 1880347072.0, d5 = 701980252875.0 / 199316789632.0,
-                          d6 = -1453857185.0 / 822651844.0, d7 = 69997945.0 / 29380423.0;
+  MP_DPK(c2, 0) MP_DPK(c3, 1) MP_DPK(c4, 2) MP_DPK(c5, 3)
+  MP_DPK(a21, 4) MP_DPK(a31, 5) MP_DPK(a32, 6) MP_DPK(a41, 7) MP_DPK(a42, 8) MP_DPK(a43, 9)
+  MP_DPK(a51, 10) MP_DPK(a52, 11) MP_DPK(a53, 12) MP_DPK(a54, 13)
+  MP_DPK(a61, 14) MP_DPK(a62, 15) MP_DPK(a63, 16) MP_DPK(a64, 17) MP_DPK(a65, 18)
+  MP_DPK(b1, 19) MP_DPK(b3, 20) MP_DPK(b4, 21) MP_DPK(b5, 22) MP_DPK(b6, 23)
+  MP_DPK(e1, 24) MP_DPK(e3, 25) MP_DPK(e4, 26) MP_DPK(e5, 27) MP_DPK(e6, 28) MP_DPK(e7, 29)
+  MP_DPK(d1, 30) MP_DPK(d3, 31) MP_DPK(d4, 32) MP_DPK(d5, 33) MP_DPK(d6, 34) MP_DPK(d7, 35)
 };
 
 // Block form of the step (the default).  A step's five new stage times depend on (t, h) only, so
@@ -860,7 +870,7 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   bool last = false;
   if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
   const double tn = last ? t_end : t + h;
-  const double ts[5] = {fma(DP::c2, h, t), fma(DP::c3, h, t), fma(DP::c4, h, t), fma(DP::c5, h, t), tn};
+  const double ts[5] = {fma(DP::c2(), h, t), fma(DP::c3(), h, t), fma(DP::c4(), h, t), fma(DP::c5(), h, t), tn};
   // ---- disc block
   double u[5];
   TableAt ta[5];
@@ -902,20 +912,20 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   }
   // ---- spin chain
   const double k1 = in.k1;
-  const double y2 = fma(h, DP::a21 * k1, y);
+  const double y2 = fma(h, DP::a21() * k1, y);
   const double k2 = spin_f(sp, w, d[0], y2);
-  const double y3 = fma(h, fma(DP::a32, k2, DP::a31 * k1), y);
+  const double y3 = fma(h, fma(DP::a32(), k2, DP::a31() * k1), y);
   const double k3 = spin_f(sp, w, d[1], y3);
-  const double y4 = fma(h, fma(DP::a43, k3, fma(DP::a42, k2, DP::a41 * k1)), y);
+  const double y4 = fma(h, fma(DP::a43(), k3, fma(DP::a42(), k2, DP::a41() * k1)), y);
   const double k4 = spin_f(sp, w, d[2], y4);
-  const double y5 = fma(h, fma(DP::a54, k4, fma(DP::a53, k3, fma(DP::a52, k2, DP::a51 * k1))), y);
+  const double y5 = fma(h, fma(DP::a54(), k4, fma(DP::a53(), k3, fma(DP::a52(), k2, DP::a51() * k1))), y);
   const double k5 = spin_f(sp, w, d[3], y5);
-  const double y6 = fma(h, fma(DP::a65, k5, fma(DP::a64, k4, fma(DP::a63, k3, fma(DP::a62, k2, DP::a61 * k1)))), y);
+  const double y6 = fma(h, fma(DP::a65(), k5, fma(DP::a64(), k4, fma(DP::a63(), k3, fma(DP::a62(), k2, DP::a61() * k1)))), y);
   const double k6 = spin_f(sp, w, d[4], y6);
-  const double ynew = fma(h, fma(DP::b6, k6, fma(DP::b5, k5, fma(DP::b4, k4, fma(DP::b3, k3, DP::b1 * k1)))), y);
+  const double ynew = fma(h, fma(DP::b6(), k6, fma(DP::b5(), k5, fma(DP::b4(), k4, fma(DP::b3(), k3, DP::b1() * k1)))), y);
   const double k7 = spin_f(sp, w, d[4], ynew);
   in.n_rhs += 6;
-  const double esum = fma(DP::e7, k7, fma(DP::e6, k6, fma(DP::e5, k5, fma(DP::e4, k4, fma(DP::e3, k3, DP::e1 * k1)))));
+  const double esum = fma(DP::e7(), k7, fma(DP::e6(), k6, fma(DP::e5(), k5, fma(DP::e4(), k4, fma(DP::e3(), k3, DP::e1() * k1)))));
   const double errv = h * esum;
   const double sk = sp.rtol * fmax(fabs(y), fabs(ynew));
   const double aerr = fabs(errv);
@@ -930,7 +940,7 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
     const double hnew = h / (double)fac;
     in.facold = fmaxf(errf, 1.0e-4f);
     // dense output (Hairer's contd5)
-    const double dsum = fma(DP::d7, k7, fma(DP::d6, k6, fma(DP::d5, k5, fma(DP::d4, k4, fma(DP::d3, k3, DP::d1 * k1)))));
+    const double dsum = fma(DP::d7(), k7, fma(DP::d6(), k6, fma(DP::d5(), k5, fma(DP::d4(), k4, fma(DP::d3(), k3, DP::d1() * k1)))));
     const double ydiff = ynew - y;
     const double bspl = fma(h, k1, -ydiff);
     in.r1 = y;
