@@ -21,7 +21,10 @@
 
 namespace mp {
 
-constexpr int kNB = 32;  // nodes buffered per thread between phase A and phase B
+#ifndef MP_KNB
+#define MP_KNB 16
+#endif
+constexpr int kNB = MP_KNB;  // nodes buffered per thread between phase A and phase B
 
 struct KernelArgs {
   Spec sp;
