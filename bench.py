@@ -38,12 +38,12 @@ import numpy as np
 DATASETS = ("Classic", "Sloped", "Stuttering")
 METRIC = "walker_lnprob_evals_per_sec"
 UNIT = "evals/s"
-F_RHS, F_LUM, F_CHI = 440.0, 400.0, 12.0      # algorithmic FP64 flop per unit
-# What the kernel actually executes, from ncu (profiles/r01_v4_eval_kernel_ncu_full.csv):
-# (2*DFMA + DADD + DMUL thread instructions) / (walkers * RHS evaluations) = 141.6 flop per RHS
-# evaluation, 88.8 FP64 instructions per RHS evaluation; FP64 pipe 42.6 % active.
-EXECUTED_FLOP_PER_RHS_NCU = 141.6
-FP64_PIPE_ACTIVE_PCT_NCU = 42.6
+F_RHS, F_LUM, F_CHI = 440.0, 400.0, 12.0      # flop per unit of the REFERENCE's formulation
+# What the kernel executes per right-hand-side evaluation, counted by ncu on this workload
+# (profiles/r01_executed.json, written from the committed ncu capture by tools/ncu_digest.py):
+# flop = 2*DFMA + DMUL + DADD thread instructions / (walkers * RHS evaluations).
+with open(os.path.join(ROOT, "profiles", "r01_executed.json")) as _f:
+    NCU = json.load(_f)
 
 
 def parse():
@@ -52,7 +52,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ensembles", type=int, default=1024, help="independent 256-walker ensembles per dataset per GPU")
+    ap.add_argument("--ensembles", type=int, default=1184,
+                    help="independent 256-walker ensembles per dataset per GPU (1184 = 148 SMs x 8 resident blocks: "
+                         "the launch is a whole number of waves)")
     ap.add_argument("--nwalk", type=int, default=256)
     ap.add_argument("--cpu-evals", type=int, default=0, help="CPU-baseline sample size (0: ~16 per core)")
     ap.add_argument("--no-extra", action="store_true")
@@ -109,7 +111,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_step = 16 * cores          # ~0.5 s of CPU work per step on this box
+    per_step = 64 * cores          # ~2 s of CPU work per step on this box
     import scipy
     vals = []
     for s in range(args.warmup + args.steps):
@@ -258,8 +260,9 @@ def run_ours(args):
     achieved = (value / world) * flop_per_eval / 1e12
 
     # ---- e2e through the host-pointer C-ABI call -------------------------------------
-    np_theta = {n: host_theta[n].numpy() for n in DATASETS}
-    out_h = {n: np.empty(W) for n in DATASETS}
+    np_theta = {n: host_theta[n].numpy() for n in DATASETS}                       # pinned
+    out_pin = {n: torch.empty(W, dtype=torch.float64).pin_memory() for n in DATASETS}
+    out_h = {n: out_pin[n].numpy() for n in DATASETS}
 
     def e2e_step():
         for n in DATASETS:
@@ -281,35 +284,45 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu:
-        n_cpu = args.cpu_evals or 16 * (os.cpu_count() or 1)
+        n_cpu = args.cpu_evals or 320 * (os.cpu_count() or 1)   # ~10 s of host work
         v, dt, procs = cpu_throughput(n_cpu)
         import scipy
         cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
                "sample": f"{n_cpu} lnprob evaluations of the same walker draws in {dt:.1f} s, multiprocessing.Pool({procs}); "
                          f"oracle = scipy {scipy.__version__} odeint restatement of the reference path"}
 
+    # FP64 roofline of eval_kernel: executed flop (ncu-counted per RHS evaluation, RHS evaluations
+    # counted live on the device) over the live-measured launch time, against the live DFMA peak.
+    rhs_per_s = (value / world) * mean_nrhs
+    executed = rhs_per_s * NCU["flop_per_rhs"] / 1e12
+    roofline = {
+        "bound": "fp64", "achieved": executed, "peak": peak, "unit": "TFLOP/s",
+        "frac": executed / peak if peak else None,
+        "traffic": NCU.get("dram_bytes_per_launch"),
+        "kernel": "mp::eval_kernel<kModeLnprob,64>",
+        "how": "achieved = (RHS evaluations/s, counted on the device) x (FP64 flop per RHS evaluation that the kernel "
+               "executes, ncu: 2*DFMA+DMUL+DADD); peak = live DFMA micro-benchmark on this GPU (MEASURED_PEAKS.json "
+               "has no FP64 entry); launch time from CUDA events on the launching stream",
+        "flop_per_rhs_executed": NCU["flop_per_rhs"], "fp64_inst_per_rhs": NCU["fp64_inst_per_rhs"],
+        "fp64_pipe_active_pct_ncu": NCU["fp64_pipe_active_pct"], "ncu_source": NCU["source"],
+        "mean_rhs_per_eval": mean_nrhs, "hbm_bytes_per_eval": 48 + 8 + 4,
+        "survey_8d_convention": {
+            "note": "SURVEY.md 8(d) counts the reference's formulation (440 flop per RHS: generic pow/tanh/sqrt); "
+                    "the kernel's closed-form disc mass and hoisted constants need about a third of that, so this "
+                    "figure can exceed the hardware peak and is reported for comparison only",
+            "flop_per_eval": flop_per_eval, "tflops": achieved, "frac": achieved / peak if peak else None},
+    }
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
-                         "kernel": "mp::eval_kernel<kModeLnprob>",
-                         "algorithmic_flop_per_eval": flop_per_eval, "mean_rhs_per_eval": mean_nrhs,
-                         "peak_source": "live DFMA micro-benchmark (mp_fp64_peak_tflops); MEASURED_PEAKS.json has no FP64 entry",
-                         "hbm_bytes_per_eval": 48 + 8 + 4,
-                         "note": "achieved/frac use the SURVEY 8(d) ALGORITHMIC convention (440 flop per RHS of the "
-                                 "reference's formulation); the kernel's hoisted formulation executes far fewer -- see executed_*",
-                         "executed_flop_per_rhs_ncu": EXECUTED_FLOP_PER_RHS_NCU,
-                         "executed_tflops": (value / world) * mean_nrhs * EXECUTED_FLOP_PER_RHS_NCU / 1e12,
-                         "executed_frac": ((value / world) * mean_nrhs * EXECUTED_FLOP_PER_RHS_NCU / 1e12) / peak if peak else None,
-                         "fp64_pipe_active_pct_ncu": FP64_PIPE_ACTIVE_PCT_NCU},
+            "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * 6 * 8 * len(DATASETS),
                     "d2h_bytes_per_step": W * 8 * len(DATASETS)},
-            "gpu_launches": 2 * args.steps * len(DATASETS),   # explicit launch + stiff-bucket launch per dataset
+            "gpu_launches": 2 * args.steps * len(DATASETS),   # eval_kernel + eval_stiff_kernel per dataset per step
             "clocks": clocks,
             "nonfinite_lnprob": bad,
             "wall_s_timed_region": wall,

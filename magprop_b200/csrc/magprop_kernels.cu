@@ -354,11 +354,17 @@ struct mp_handle {
   double *s_theta = nullptr, *s_out = nullptr, *s_state = nullptr, *s_lnp = nullptr;
   int *s_status = nullptr, *s_nrhs = nullptr;
   size_t cap_theta = 0, cap_out = 0, cap_state = 0, cap_w = 0;
-  int* d_queue = nullptr;      // walkers deferred to the stiff launch
-  int* d_queue_count = nullptr;
-  size_t cap_queue = 0;
+  // Two pipeline lanes: each has its own stream and its own stiff-walker queue, so that the
+  // host-pointer entry points can overlap the H2D copy of one chunk with the kernel of the previous
+  // one.  Device-pointer entry points use lane 0's queue on the caller's stream.
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    int* queue = nullptr;        // walkers deferred to the stiff launch
+    int* queue_count = nullptr;
+    size_t cap_queue = 0;
+  } lanes[2];
   int sm_count = 148;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // == lanes[0].stream
 };
 
 template <typename T>
@@ -419,10 +425,15 @@ extern "C" int mp_create(const mp_model_spec* spec, const mp_prior_spec* prior, 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
   }
-  if (cudaMalloc((void**)&h->d_queue_count, sizeof(int)) != cudaSuccess) {
-    delete h;
-    return fail(MP_ERR_CUDA, "mp_create: cudaMalloc failed");
+  for (auto& L : h->lanes) {
+    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc((void**)&L.queue_count, sizeof(int)) != cudaSuccess ||
+        cudaMemset(L.queue_count, 0, sizeof(int)) != cudaSuccess) {
+      mp_destroy(h);
+      return fail(MP_ERR_CUDA, "mp_create: stream / queue allocation failed");
+    }
   }
+  h->stream = h->lanes[0].stream;
   h->D = D;
   h->np = np;
   h->data_nodes.n_nodes = (int)np.node_t.size();
@@ -446,7 +457,10 @@ extern "C" void mp_destroy(mp_handle* h) {
   for (auto& kv : h->curve_nodes) cudaFree(kv.second.node_t);
   cudaFree(h->s_theta); cudaFree(h->s_out); cudaFree(h->s_state); cudaFree(h->s_lnp);
   cudaFree(h->s_status); cudaFree(h->s_nrhs);
-  cudaFree(h->d_queue); cudaFree(h->d_queue_count);
+  for (auto& L : h->lanes) {
+    cudaFree(L.queue); cudaFree(L.queue_count);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
   delete h;
 }
 
@@ -486,12 +500,13 @@ static int fill_args(mp_handle* h, KernelArgs& a, const DeviceNodes& nodes, bool
   return MP_OK;
 }
 
-static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream) {
-  int rc = ensure(&h->d_queue, &h->cap_queue, (size_t)W);
+static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream, int lane = 0) {
+  mp_handle::Lane& L = h->lanes[lane];
+  int rc = ensure(&L.queue, &L.cap_queue, (size_t)W);
   if (rc) return rc;
-  a.queue = h->d_queue;
-  a.queue_count = h->d_queue_count;
-  MP_CUDA(cudaMemsetAsync(h->d_queue_count, 0, sizeof(int), stream));
+  a.queue = L.queue;
+  a.queue_count = L.queue_count;
+  MP_CUDA(cudaMemsetAsync(L.queue_count, 0, sizeof(int), stream));
   return MP_OK;
 }
 
@@ -504,9 +519,9 @@ static int stiff_grid(const mp_handle* h, int W, int block) {
 }
 
 template <int MODE>
-static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream) {
+static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane = 0) {
   if (a.W == 0) return MP_OK;
-  int rc = prepare_queue(h, a, a.W, stream);
+  int rc = prepare_queue(h, a, a.W, stream, lane);
   if (rc) return rc;
   // small ensembles: 32-thread blocks spread the warps over more SMs
   if (a.W <= 148 * 64 * 4) {
@@ -534,6 +549,9 @@ extern "C" int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32
   return launch_eval<kModeLnprob>(h, a, (cudaStream_t)stream);
 }
 
+// One full wave of the explicit kernel: 8 resident 64-thread blocks per SM.
+static int wave_walkers(const mp_handle* h) { return h->sm_count * MP_MIN_BLOCKS_64 * 64; }
+
 extern "C" int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int32_t ndim, double* lnp,
                                int32_t* status, int32_t* n_rhs) {
   if (!h || (W > 0 && (!theta || !lnp))) return fail(MP_ERR_BAD_ARG, "mp_lnprob_batch: null pointer");
@@ -550,13 +568,34 @@ extern "C" int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int
     MP_CUDA(cudaMalloc((void**)&h->s_nrhs, (size_t)W * sizeof(int)));
     h->cap_w = W;
   }
-  MP_CUDA(cudaMemcpyAsync(h->s_theta, theta, (size_t)W * ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  rc = mp_lnprob_batch_device(h, h->s_theta, W, ndim, h->s_lnp, h->s_status, h->s_nrhs, h->stream);
-  if (rc) return rc;
-  MP_CUDA(cudaMemcpyAsync(lnp, h->s_lnp, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (status) MP_CUDA(cudaMemcpyAsync(status, h->s_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  if (n_rhs) MP_CUDA(cudaMemcpyAsync(n_rhs, h->s_nrhs, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  MP_CUDA(cudaStreamSynchronize(h->stream));
+  // Large batches go through in wave-sized chunks on two alternating lanes: the H2D copy of chunk
+  // k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k (when the caller's buffers are
+  // pinned; pageable buffers still work, the copies just serialise).
+  const int wave = wave_walkers(h);
+  const int chunk = (W <= wave + wave / 2) ? W : wave;
+  KernelArgs a;
+  if ((rc = fill_args(h, a, h->data_nodes, true, ndim, W, true))) return rc;
+  int k = 0;
+  for (int c0 = 0; c0 < W; c0 += chunk, ++k) {
+    const int lane = k & 1;
+    cudaStream_t st = h->lanes[lane].stream;
+    int n = W - c0;
+    if (n > chunk + chunk / 2) n = chunk;          // the last chunk absorbs a remainder below half a wave
+    MP_CUDA(cudaMemcpyAsync(h->s_theta + (size_t)c0 * ndim, theta + (size_t)c0 * ndim, (size_t)n * ndim * sizeof(double),
+                            cudaMemcpyHostToDevice, st));
+    a.W = n;
+    a.theta = h->s_theta + (size_t)c0 * ndim;
+    a.lnp = h->s_lnp + c0;
+    a.status = h->s_status + c0;
+    a.n_rhs = h->s_nrhs + c0;
+    if ((rc = launch_eval<kModeLnprob>(h, a, st, lane))) return rc;
+    MP_CUDA(cudaMemcpyAsync(lnp + c0, h->s_lnp + c0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (status) MP_CUDA(cudaMemcpyAsync(status + c0, h->s_status + c0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (n_rhs) MP_CUDA(cudaMemcpyAsync(n_rhs + c0, h->s_nrhs + c0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (n != chunk) break;
+  }
+  MP_CUDA(cudaStreamSynchronize(h->lanes[0].stream));
+  MP_CUDA(cudaStreamSynchronize(h->lanes[1].stream));
   return MP_OK;
 }
 
@@ -728,7 +767,7 @@ extern "C" int mp_last_stiff_count(mp_handle* h, int32_t* count) {
   if (!h || !count) return fail(MP_ERR_BAD_ARG, "mp_last_stiff_count: null pointer");
   MP_CUDA(cudaSetDevice(h->device));
   MP_CUDA(cudaDeviceSynchronize());
-  MP_CUDA(cudaMemcpy(count, h->d_queue_count, sizeof(int), cudaMemcpyDeviceToHost));
+  MP_CUDA(cudaMemcpy(count, h->lanes[0].queue_count, sizeof(int), cudaMemcpyDeviceToHost));
   return MP_OK;
 }
 
