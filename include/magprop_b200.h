@@ -64,7 +64,7 @@ typedef struct mp_model_spec {
   int32_t lprop_binding_term; /* 1: Lprop = propeff*(-Nacc*w - GM/Rm*eta2*Mdot) (funcs.py:222-223); 0: propeff*(-Nacc*w) (magnetar/funcs.py:206) */
   int32_t unlog_mask;      /* bit i set: theta[i] is log10 and is un-logged before the model (mcmc_eqns.py:17: bits 2..5) */
   double rtol;             /* relative tolerance of the spin integrator (0 => default 1e-10) */
-  int32_t max_steps;       /* step budget per walker (0 => default 200000)                  */
+  int32_t max_steps;       /* step budget per walker (0 => default 50000)                   */
   int32_t reserved;
 } mp_model_spec;
 
