@@ -478,54 +478,6 @@ MP_HD double spin_rhs(const Spec& sp, const Walker& w, const DiscAt& d, double o
   return fma(-w.Cdip_I * om2, omega, nacc * sp.inv_inertia);
 }
 
-// Break-up sliding mode.  N_acc is switched off above rot_param = breakup_rhs (funcs.py:131-132).
-// If the spin reaches that boundary while the accretion torque still outweighs the dipole torque,
-// the solution chatters across the discontinuity (a Filippov sliding mode): LSODA burns its step
-// budget there and the reference returns 'flag' -> -inf (funcs.py:172-173).  We detect the
-// crossing and fail at once instead of taking 1e5 tiny steps to the same verdict.
-MP_HD bool breakup_sliding(const Spec& sp, const Walker& w, const DiscAt& d, double y_old, double y_new);
-
-// f and J = df/d(omega) together (implicit stages of the stiff integrator).
-MP_HD void spin_rhs_jac(const Spec& sp, const Walker& w, const DiscAt& d, double omega, double& f, double& J) {
-  double fast, lever, dfast, dlever;
-  if (d.rm * omega >= w.kc) {
-    const double r = rsqrt_fast(omega);
-    const double hio = -0.5 * r * r;                 // -1/(2 omega)
-    fast = w.Ccap * r;
-    dfast = fast * hio;
-    if (w.kc >= kR * omega) { lever = w.sGMkc * r; dlever = lever * hio; }
-    else { lever = sp.sqrt_GMR; dlever = 0.0; }
-  } else {
-    fast = d.wq * omega;
-    dfast = d.wq;
-    lever = (d.rm >= kR) ? w.sGMA * d.q : sp.sqrt_GMR;
-    dlever = 0.0;
-  }
-  const double om2 = omega * omega;
-  double nacc = 0.0, dnacc = 0.0;
-  if (!(om2 > sp.omega2_breakup_rhs)) {
-    const double x = sp.rhs_n * (fast - 1.0);
-    double th = 1.0, sech2 = 0.0;
-    if (!(x > 19.1)) {
-      const double r = rcp_fast(exp_c(2.0 * x) + 1.0);
-      th = fma(-2.0, r, 1.0);
-      sech2 = 4.0 * r * (1.0 - r);
-    }
-    nacc = -lever * d.mdot * th;
-    dnacc = -d.mdot * fma(dlever, th, lever * sp.rhs_n * sech2 * dfast);
-  }
-  f = fma(-w.Cdip_I * om2, omega, nacc * sp.inv_inertia);
-  J = fma(-3.0 * w.Cdip_I, om2, dnacc * sp.inv_inertia);
-}
-
-MP_HD bool breakup_sliding(const Spec& sp, const Walker& w, const DiscAt& d, double y_old, double y_new) {
-  const bool above_old = y_old * y_old > sp.omega2_breakup_rhs;
-  const bool above_new = y_new * y_new > sp.omega2_breakup_rhs;
-  if (above_old == above_new) return false;
-  const double om_c = sqrt(sp.omega2_breakup_rhs) * (1.0 - 1.0e-12);   // just inside: N_acc on
-  return spin_rhs(sp, w, d, om_c) > 0.0;
-}
-
 // Luminosity stage at one node (erg/s, not yet /1e50): funcs.py:175-229.
 struct Lum { double tot, prop, dip; };
 
@@ -653,21 +605,6 @@ MP_HD double spin_f(const Spec& sp, const Walker& w, const StageDisc& d, double 
 
 // ---- Dormand-Prince 5(4) with dense output --------------------------------
 // Coefficients: Dormand & Prince 1980; dense output: Hairer, Norsett & Wanner II.6.
-// "Push" form: once k_j is known it is added straight into the running sums of the
-// stages that will use it, so no k_j has to be kept (no register shuffles, no local
-// memory).  Row j-1 holds, for source stage j = 1..7:
-//   [0..5]  a(j+1, j) ... a(j+6, j)   (stage 7 = the 5th-order weights b; 0 beyond it)
-//   [6]     e_j   (embedded error weights)        [7]  d_j  (dense-output weights)
-MP_CONST_QUALIFIER double kPush[7][8] = {
-    {1.0 / 5, 3.0 / 40, 44.0 / 45, 19372.0 / 6561, 9017.0 / 3168, 35.0 / 384, 71.0 / 57600, -12715105075.0 / 11282082432.0},
-    {9.0 / 40, -56.0 / 15, -25360.0 / 2187, -355.0 / 33, 0.0, 0.0, 0.0, 0.0},
-    {32.0 / 9, 64448.0 / 6561, 46732.0 / 5247, 500.0 / 1113, 0.0, 0.0, -71.0 / 16695, 87487479700.0 / 32700410799.0},
-    {-212.0 / 729, 49.0 / 176, 125.0 / 192, 0.0, 0.0, 0.0, 71.0 / 1920, -10690763975.0 / 1880347072.0},
-    {-5103.0 / 18656, -2187.0 / 6784, 0.0, 0.0, 0.0, 0.0, -17253.0 / 339200, 701980252875.0 / 199316789632.0},
-    {11.0 / 84, 0.0, 0.0, 0.0, 0.0, 0.0, 22.0 / 525, -1453857185.0 / 822651844.0},
-    {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, -1.0 / 40, 69997945.0 / 29380423.0}};
-MP_CONST_QUALIFIER double kCn[7] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1, 1};
-
 // State of the spin integration of one walker.
 struct Integrator {
   double t, omega, h, k1;        // k1 = f(t, omega) (FSAL)
@@ -676,9 +613,11 @@ struct Integrator {
   // dense output of the last accepted step: omega(t0 + theta*hs)
   double t0, hs, r1, r2, r3, r4, r5;   // covers [t0, t]
   int n_rhs, n_steps, status;
-  // stiffness switch: DP5 <-> Radau IIA
-  int stiff;                     // 1: take implicit steps
-  int stiff_votes;               // consecutive steps voting to change mode
+  int stiff;                     // explicit variant: stiffness detected (the walker is deferred)
+  int stiff_votes;               // consecutive steps voting stiff
+  // implicit variant only: f, df/domega and the disc quantities at (t, omega), carried from step to step
+  double J0, d0_qa, d0_ni;
+  int have0;
 };
 
 MP_HD double dense_eval(const Integrator& in, double tq) {
@@ -706,6 +645,8 @@ MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, doub
   in.n_steps = 0;
   in.stiff = 0;
   in.stiff_votes = 0;
+  in.have0 = 0;
+  in.J0 = in.d0_qa = in.d0_ni = 0.0;
   in.status = kWalkerOk;
   in.t0 = t_start; in.hs = 1.0;
   in.r1 = w.omega0; in.r2 = in.r3 = in.r4 = in.r5 = 0.0;
@@ -743,103 +684,6 @@ MP_HD void controller(float err, float facold, float& fac11, float& fac) {
 #endif
 }
 
-// Attempt one step; on acceptance advances (t, omega) and refreshes the dense
-// output.  Returns true when a step was accepted.  (Rolled push-form variant: one inlined copy of
-// disc_at + f in a 5-trip loop; kept for A/B measurements, -DMP_STEP_ROLLED.)
-MP_HD bool integrator_step_rolled(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
-  const double t = in.t, y = in.omega;
-  double h = in.h;
-  bool last = false;
-  if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
-  const double tn = last ? t_end : t + h;
-  const double k1 = in.k1;
-  // running sums for the next six stages, the error estimate and the dense output
-  double a0 = kPush[0][0] * k1, a1 = kPush[0][1] * k1, a2 = kPush[0][2] * k1, a3 = kPush[0][3] * k1,
-         a4 = kPush[0][4] * k1, a5 = kPush[0][5] * k1;
-  double esum = kPush[0][6] * k1, dsum = kPush[0][7] * k1;
-  DiscAt m;
-  double y6 = y, k6 = k1;
-  // One inlined copy of disc_at + f serves the five stages that need a new time; the FSAL
-  // stage (k7, same time as stage 6) is peeled so that nothing extra stays live in the loop.
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-  for (int s = 1; s <= 5; ++s) {
-    const double ys = fma(h, a0, y);
-    m = disc_at(w, (s == 5) ? tn : fma(kCn[s], h, t));
-    const double f = spin_rhs(sp, w, m, ys);
-    const double* c = kPush[s];
-    a0 = fma(c[0], f, a1);
-    a1 = fma(c[1], f, a2);
-    a2 = fma(c[2], f, a3);
-    a3 = fma(c[3], f, a4);
-    a4 = fma(c[4], f, a5);
-    a5 = 0.0;
-    esum = fma(c[6], f, esum);
-    dsum = fma(c[7], f, dsum);
-    y6 = ys;
-    k6 = f;
-  }
-  const double ynew = fma(h, a0, y);
-  const double k7 = spin_rhs(sp, w, m, ynew);
-  esum = fma(kPush[6][6], k7, esum);
-  dsum = fma(kPush[6][7], k7, dsum);
-  in.n_rhs += 6;
-  const double errv = h * esum;
-  const double sk = sp.rtol * fmax(fabs(y), fabs(ynew));
-  const double aerr = fabs(errv);
-  const bool accept = aerr <= sk;                 // false for NaN
-  float errf = (float)aerr / (float)sk;
-  if (!(errf == errf)) errf = 1.0e10f;            // NaN => shrink hard
-  float fac11, fac;
-  controller(errf, in.facold, fac11, fac);
-  const float safe = 0.9f, facc1 = 5.0f, facc2 = 0.1f;   // h may shrink 5x, grow 10x
-  if (accept) {
-    fac = fmaxf(facc2, fminf(facc1, fac / safe));
-    double hnew = h / (double)fac;
-    in.facold = fmaxf(errf, 1.0e-4f);
-    // dense output
-    const double ydiff = ynew - y;
-    const double bspl = fma(h, k1, -ydiff);
-    in.r1 = y;
-    in.r2 = ydiff;
-    in.r3 = bspl;
-    in.r4 = ydiff - h * k7 - bspl;
-    in.r5 = h * dsum;
-    in.t0 = t; in.hs = h;
-    in.t = tn;
-    in.omega = ynew;
-    in.k1 = k7;
-#ifndef MP_NO_SLIDING
-    if (breakup_sliding(sp, w, m, y, ynew)) in.status = kWalkerIntegratorFail;
-#endif
-    in.h = in.rejected ? fmin(hnew, h) : hnew;
-    in.rejected = 0;
-    in.n_steps++;
-    // stiffness detection: h*|lambda| estimated from the last two stages, which share t_n + h
-    // (Hairer's dopri5 device).  The controller holds a stiff walker near h*|lambda| ~ 2 (the error
-    // estimate grows before the stability limit 3.3 is reached), i.e. at steps far smaller than
-    // the time scale t on which the solution itself varies.  12 such steps in a row hand the
-    // walker to the implicit integrator.
-#ifndef MP_NO_VOTES
-    const double dy = fabs(ynew - y6);
-    if (fabs(k7 - k6) * tn > 30.0 * dy && h < 0.02 * tn) {   // |lambda| t > 30 while h << t
-      if (++in.stiff_votes >= 12) { in.stiff = 1; in.stiff_votes = 0; }
-    } else {
-      in.stiff_votes = 0;
-    }
-#endif
-    return true;
-  }
-  // rejected
-  const double hnew = h / (double)fminf(facc1, fac11 / safe);
-  in.h = hnew;
-  in.rejected = 1;
-  in.n_steps++;
-  if (!(fabs(hnew) > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
-  return false;
-}
-
 // Dormand-Prince tableau (classic form) for the block step, as constant-bank operands.
 MP_CONST_QUALIFIER double kDP[36] = {
     1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9,                                                   // 0: c2..c5
@@ -868,10 +712,12 @@ struct DP {
 // polynomials, exponentials and x^(-1/7) before it -- is evaluated first as one block of
 // independent chains (that is where the FP64 pipe gets saturated); the six evaluations of the
 // scalar spin equation, which are inherently serial, follow as one straight-line chain.
-// Break-up sliding mode, block-step form (see breakup_sliding).  Called when the evaluations of a
-// step straddled the break-up boundary.  The walker slides if, just inside the boundary, the
-// accretion torque still outweighs the dipole torque (N_acc switches off above it, funcs.py:131,
-// so the state can neither cross nor leave).  An accepted step that crossed is judged at once; a
+// Break-up sliding mode.  N_acc is switched off above rot_param = breakup_rhs (funcs.py:131-132).
+// If the spin reaches that boundary while, just inside it, the accretion torque still outweighs the
+// dipole torque, the state can neither cross nor leave: the solution chatters along the
+// discontinuity (a Filippov sliding mode).  LSODA burns its step budget there and the reference
+// returns 'flag' -> -inf (funcs.py:172-173); we detect the situation and fail at once.  Called when
+// the evaluations of a step straddled the boundary.  An accepted step that crossed is judged at once; a
 // step that only sampled the far side with its stages is judged once the state sits within 1e-6
 // of the boundary -- the integrator otherwise realises the sliding mode numerically, hovering
 // rtol below the boundary with steps of 1e-8 t (measured: 78 000 steps for one such walker).
@@ -963,6 +809,48 @@ MP_HD bool step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, cons
   return false;
 }
 
+// Disc quantities at N stage times, evaluated as one block of independent chains.
+template <int N>
+MP_HD void disc_stages(const Walker& w, const double* ts, StageDisc* d) {
+  double u[N];
+  TableAt ta[N];
+  bool in_all = true;
+#pragma unroll
+  for (int s = 0; s < N; ++s) {
+    u[s] = fma(ts[s], w.inv_tv, w.eps);
+    in_all = table_locate_safe(u[s], ta[s]) && in_all;
+  }
+  if (in_all && u[0] >= w.u_late) {
+    // late phase: S and Q = S^(-1/7) from the same table row -- no exp, no log
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+      const double s2 = ta[s].s * ta[s].s;
+      const double S = poly10p(ta[s].row, ta[s].s, s2);
+      const double Q = poly10p(ta[s].row + MP_DISC_ROW, ta[s].s, s2);
+      d[s].ni = (w.K * S) * w.tvI;
+      d[s].qa = w.KqA * Q;
+    }
+  } else {
+    double S[N];
+#pragma unroll
+    for (int s = 0; s < N; ++s) S[s] = poly10p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
+    if (!in_all) {                                      // parameters far outside the prior box
+#pragma unroll
+      for (int s = 0; s < N; ++s) {
+        TableAt tb;
+        if (!table_locate(u[s], tb)) S[s] = disc_S_outside(u[s], tb.e);
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < N; ++s) {
+      const double E = exp_c(w.u0 - u[s]);
+      const double M = fma(w.K, S[s], w.C * E);
+      d[s].ni = M * w.tvI;
+      d[s].qa = w.sqrtA * pow_m17_fast(M);
+    }
+  }
+}
+
 MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
   const double t = in.t, y = in.omega;
   double h = in.h;
@@ -974,45 +862,8 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   in.r1 = in.r2 = in.r3 = in.r4 = in.r5 = 0.0;
   in.t0 = t;
   const double ts[5] = {fma(DP::c2(), h, t), fma(DP::c3(), h, t), fma(DP::c4(), h, t), fma(DP::c5(), h, t), tn};
-  // ---- disc block
-  double u[5];
-  TableAt ta[5];
-  bool in_all = true;
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    u[s] = fma(ts[s], w.inv_tv, w.eps);
-    in_all = table_locate_safe(u[s], ta[s]) && in_all;
-  }
   StageDisc d[5];
-  if (in_all && u[0] >= w.u_late) {
-    // late phase: S and Q = S^(-1/7) from the same table row -- no exp, no log
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      const double s2 = ta[s].s * ta[s].s;
-      const double S = poly10p(ta[s].row, ta[s].s, s2);
-      const double Q = poly10p(ta[s].row + MP_DISC_ROW, ta[s].s, s2);
-      d[s].ni = (w.K * S) * w.tvI;
-      d[s].qa = w.KqA * Q;
-    }
-  } else {
-    double S[5];
-#pragma unroll
-    for (int s = 0; s < 5; ++s) S[s] = poly10p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
-    if (!in_all) {                                      // parameters far outside the prior box
-#pragma unroll
-      for (int s = 0; s < 5; ++s) {
-        TableAt tb;
-        if (!table_locate(u[s], tb)) S[s] = disc_S_outside(u[s], tb.e);
-      }
-    }
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      const double E = exp_c(w.u0 - u[s]);
-      const double M = fma(w.K, S[s], w.C * E);
-      d[s].ni = M * w.tvI;
-      d[s].qa = w.sqrtA * pow_m17_fast(M);
-    }
-  }
+  disc_stages<5>(w, ts, d);
   // (One shared copy of the chain: inlining it after each disc block lets the compiler overlap the
   // two, but lanes of a warp that sit in different phases then run the chain twice -- measured
   // 4 % slower on uniform ensembles, 11 % on spread ones.)
@@ -1038,39 +889,77 @@ struct RadauC {
   static constexpr double dd1 = -(13.0 + 7.0 * s6) / 3.0, dd2 = (-13.0 + 7.0 * s6) / 3.0, dd3 = -1.0 / 3.0;
 };
 
-#if defined(__CUDACC__)
-__device__ __host__ __noinline__
-#endif
-static Integrator radau_step(const Spec sp, const Walker w, double t_end, Integrator in) {
-  // Everything by value: a reference here would pin the caller's Integrator/Walker to local
-  // memory for the whole kernel, slowing the explicit path that never comes here.
+// f and J = df/d(omega) in the folded, branch-free form of spin_f.
+MP_HD void spin_fJ(const Spec& sp, const Walker& w, const StageDisc& d, double omega, double& f, double& J,
+                   unsigned& side) {
+  const double rm = d.qa * d.qa;
+  const double r = rsqrt_pos(omega);
+  const double hio = -0.5 * (r * r);                           // -1/(2 omega)
+  const bool capped = rm * omega >= sp.kc;
+  const double wq = (rm * d.qa) * sp.inv_sqrtGM;
+  const double fast_c = sp.Ccap * r;
+  const double fast = capped ? fast_c : wq * omega;
+  const double dfast = capped ? fast_c * hio : wq;
+  const double lev_u = (rm < kR) ? sp.sqrt_GMR : sp.sqrtGM * d.qa;
+  const bool lc_var = sp.kc >= kR * omega;
+  const double lev_c = lc_var ? sp.sGMkc * r : sp.sqrt_GMR;
+  const double lever = capped ? lev_c : lev_u;
+  const double dlever = (capped && lc_var) ? lev_c * hio : 0.0;
+  const double om2 = omega * omega;
+  const double x = sp.rhs_n * (fast - 1.0);
+  double th, sech2;
+  if (x > 19.1) { th = 1.0; sech2 = 0.0; }
+  else if (x < -19.1) { th = -1.0; sech2 = 0.0; }
+  else {
+    const double rr = rcp_pos(exp_small(x + x) + 1.0);
+    th = fma(-2.0, rr, 1.0);
+    sech2 = 4.0 * rr * (1.0 - rr);
+  }
+  const bool above = om2 > sp.omega2_breakup_rhs;
+  side |= above ? 2u : 1u;
+  if (above) { th = 0.0; sech2 = 0.0; }
+  f = fma(-w.Cdip_I * om2, omega, -(lever * d.ni) * th);
+  J = fma(-3.0 * w.Cdip_I, om2, -d.ni * fma(dlever, th, lever * sp.rhs_n * sech2 * dfast));
+}
+
+// One Radau IIA step.  The implicit variant of the kernel runs every step through here (walkers
+// are bucketed: one that turns stiff under DP5 is re-run implicitly from the start, so the lanes of
+// a warp all execute this function).  f, J and the disc quantities at (t, omega) are carried over
+// from the previous step's end point.
+MP_HD void radau_step(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
   using R = RadauC;
   const double t = in.t, y = in.omega;
   double h = in.h;
   bool last = false;
   if (t + 1.01 * h >= t_end) { h = t_end - t; last = true; }
   const double tn = last ? t_end : t + h;
-  const DiscAt m0 = disc_at(w, t);
-  const DiscAt m1 = disc_at(w, fma(R::c1, h, t));
-  const DiscAt m2 = disc_at(w, fma(R::c2, h, t));
-  const DiscAt m3 = disc_at(w, tn);
-  double f0, J0;
-  spin_rhs_jac(sp, w, m0, y, f0, J0);
-  in.n_rhs += 1;
+  const double ts[3] = {fma(R::c1, h, t), fma(R::c2, h, t), tn};
+  StageDisc d[3];
+  disc_stages<3>(w, ts, d);
+  unsigned side = (y * y > sp.omega2_breakup_rhs) ? 2u : 1u;
+  if (!in.have0) {
+    StageDisc d0;
+    disc_stages<1>(w, &t, &d0);
+    in.d0_qa = d0.qa; in.d0_ni = d0.ni;
+    spin_fJ(sp, w, d0, y, in.k1, in.J0, side);
+    in.n_rhs += 1;
+    in.have0 = 1;
+  }
+  const double f0 = in.k1, J0 = in.J0;
   const double sk = sp.rtol * fabs(y);
-  // starting values: extrapolate the previous step's dense polynomial
-  double z1 = dense_eval(in, fma(R::c1, h, t)) - y;
-  double z2 = dense_eval(in, fma(R::c2, h, t)) - y;
+  // starting values: extrapolate the previous step's collocation polynomial
+  double z1 = dense_eval(in, ts[0]) - y;
+  double z2 = dense_eval(in, ts[1]) - y;
   double z3 = dense_eval(in, tn) - y;
-  if (!(fabs(z3) < 0.5 * fabs(y)) || in.rejected) { z1 = z2 = z3 = 0.0; }
+  if (!(fabs(z3) < 0.5 * fabs(y)) || in.rejected || in.n_steps == 0) { z1 = z2 = z3 = 0.0; }
   bool converged = false;
   double dz_prev = INFINITY;
   int it = 0;
   for (; it < 8; ++it) {
     double f1, f2, f3, J1, J2, J3;
-    spin_rhs_jac(sp, w, m1, y + z1, f1, J1);
-    spin_rhs_jac(sp, w, m2, y + z2, f2, J2);
-    spin_rhs_jac(sp, w, m3, y + z3, f3, J3);
+    spin_fJ(sp, w, d[0], y + z1, f1, J1, side);
+    spin_fJ(sp, w, d[1], y + z2, f2, J2, side);
+    spin_fJ(sp, w, d[2], y + z3, f3, J3, side);
     in.n_rhs += 3;
     // residual G = Z - h A f
     const double g1 = z1 - h * (R::a11 * f1 + R::a12 * f2 + R::a13 * f3);
@@ -1097,13 +986,17 @@ static Integrator radau_step(const Spec sp, const Walker w, double t_end, Integr
     dz_prev = dz;
   }
   in.n_steps++;
+  const double ynew = y + z3;
+#ifndef MP_NO_SLIDING
+  // stages on both sides of the break-up boundary: see breakup_sliding_block
+  if (side == 3u && breakup_sliding_block(sp, w, d[2], y, ynew, converged)) in.status = kWalkerIntegratorFail;
+#endif
   if (!converged) {
     in.h = 0.5 * h;
     in.rejected = 1;
     if (!(in.h > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
-    return in;
+    return;
   }
-  const double ynew = y + z3;
   // The embedded estimate is O(h^4) for an O(h^6) local error, so it is held to rtol_stiff
   // (~ rtol^(2/3)), not rtol; the parity tests bound the resulting error.
   const double skn = sp.rtol_stiff * fmax(fabs(y), fabs(ynew));
@@ -1114,7 +1007,9 @@ static Integrator radau_step(const Spec sp, const Walker w, double t_end, Integr
   double err = fabs(errv) / skn;
   if (err >= 1.0 && (in.rejected || in.n_steps <= 1)) {
     double fe, Je;
-    spin_rhs_jac(sp, w, m0, y + errv, fe, Je);
+    StageDisc d0; d0.qa = in.d0_qa; d0.ni = in.d0_ni;
+    unsigned s2 = 0u;
+    spin_fJ(sp, w, d0, y + errv, fe, Je, s2);
     in.n_rhs += 1;
     errv = (fe + comb) / den;
     err = fabs(errv) / skn;
@@ -1122,7 +1017,12 @@ static Integrator radau_step(const Spec sp, const Walker w, double t_end, Integr
   if (!(err == err)) err = 1.0e10;
   // step-size selection (radau5): order-3 estimate, safety tied to the Newton effort
   const double safe = 0.9, fac = fmin(safe, safe * 15.0 / (double)(7 + 2 * it));
-  double quot = fmax(0.125, fmin(5.0, exp(0.25 * log(fmax(err, 1.0e-30))) / fac));
+#if defined(__CUDA_ARCH__)
+  const double e4 = (double)exp2f(0.25f * __log2f(fmaxf((float)err, 1.0e-30f)));   // steers the step size only
+#else
+  const double e4 = (double)exp2f(0.25f * log2f(fmaxf((float)err, 1.0e-30f)));
+#endif
+  const double quot = fmax(0.125, fmin(5.0, e4 / fac));
   const double hnew = h / quot;
   if (err < 1.0) {
     // collocation cubic through (0,0), (c1,z1), (c2,z2), (1,z3) in the DP5 dense form
@@ -1133,25 +1033,17 @@ static Integrator radau_step(const Spec sp, const Walker w, double t_end, Integr
     in.t0 = t; in.hs = h;
     in.t = tn;
     in.omega = ynew;
-    double fn, Jn;
-    spin_rhs_jac(sp, w, m3, ynew, fn, Jn);
+    unsigned s2 = 0u;
+    spin_fJ(sp, w, d[2], ynew, in.k1, in.J0, s2);   // next step's f0, J0
+    in.d0_qa = d[2].qa; in.d0_ni = d[2].ni;
     in.n_rhs += 1;
-    in.k1 = fn;                                     // keeps DP5's FSAL slot valid for a switch back
-    if (breakup_sliding(sp, w, m3, y, ynew)) in.status = kWalkerIntegratorFail;
     in.h = in.rejected ? fmin(hnew, h) : hnew;
     in.rejected = 0;
-    // hand back to the explicit integrator once the step is no longer stability-relevant
-    if (h * fabs(Jn) < 0.5) {
-      if (++in.stiff_votes >= 4) { in.stiff = 0; in.stiff_votes = 0; in.facold = 1.0e-4f; }
-    } else {
-      in.stiff_votes = 0;
-    }
-    return in;
+    return;
   }
   in.h = hnew;
   in.rejected = 1;
   if (!(fabs(hnew) > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
-  return in;
 }
 
 // ---- parameter handling -------------------------------------------------------
@@ -1269,12 +1161,8 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
       }
       if (!MP_WARP_ANY(step)) break;
       if (step) {
-        if (STIFF && in.stiff) in = radau_step(sp, w, t_end, in);
-#if defined(MP_STEP_ROLLED)
-        else integrator_step_rolled(sp, w, t_end, in);
-#else
+        if (STIFF) radau_step(sp, w, t_end, in);
         else integrator_step(sp, w, t_end, in);
-#endif
       }
     }
 #if defined(__CUDA_ARCH__)

@@ -42,7 +42,7 @@ inline Spec make_spec(const mp_model_spec& m) {
   s.unlog_mask = m.unlog_mask;
   s.rtol = (m.rtol > 0.0) ? m.rtol : 1.0e-10;
   const char* rs = std::getenv("MP_RTOL_STIFF");   // developer knob
-  s.rtol_stiff = rs ? std::atof(rs) : 0.15 * std::pow(s.rtol, 2.0 / 3.0);
+  s.rtol_stiff = rs ? std::atof(rs) : 0.0464 * std::pow(s.rtol, 2.0 / 3.0);
   s.max_steps = (m.max_steps > 0) ? m.max_steps : 50000;
   return s;
 }

@@ -25,6 +25,8 @@ namespace mp {
 #define MP_KNB 16
 #endif
 constexpr int kNB = MP_KNB;  // nodes buffered per thread between phase A and phase B
+// curve output hands one node to each lane of the warp in phase B, so it buffers a full warp's worth
+template <int MODE> struct NodeBuf { static constexpr int n = (MODE == kModeCurves) ? 32 : kNB; };
 
 struct KernelArgs {
   Spec sp;
@@ -89,7 +91,7 @@ __device__ __forceinline__ bool eval_one(const KernelArgs& a, bool have, int w, 
     } else if (MODE == kModeModelAtData) {
       out = a.out + (size_t)w * a.dv.n_data;
     }
-    const double chi2 = evaluate_walker<MODE, kNB, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK, st, nr,
+    const double chi2 = evaluate_walker<MODE, NodeBuf<MODE>::n, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK, st, nr,
                                                           out, state, 1, a.dat_orig, warp_scratch);
     if (!STIFF && (st & kWalkerDeferred)) return true;
     if (live && MODE == kModeLnprob) {
@@ -114,7 +116,7 @@ __device__ __forceinline__ bool eval_one(const KernelArgs& a, bool have, int w, 
 template <int MODE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64))
 eval_kernel(const __grid_constant__ KernelArgs a) {
-  __shared__ double s_buf[kNB * BLOCK];
+  __shared__ double s_buf[NodeBuf<MODE>::n * BLOCK];
   __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
   __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];   // per-warp broadcast slot (curve output)
   stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta);
@@ -125,20 +127,25 @@ eval_kernel(const __grid_constant__ KernelArgs a) {
 }
 
 // Second launch: the walkers bucketed as stiff, with the implicit integrator available.
+#ifndef MP_STIFF_MIN_WARPS
+#define MP_STIFF_MIN_WARPS 12     // resident warps per SM the implicit variant is compiled for
+#endif
 template <int MODE, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) eval_stiff_kernel(const __grid_constant__ KernelArgs a) {
-  __shared__ double s_buf[kNB * BLOCK];
+__global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) eval_stiff_kernel(const __grid_constant__ KernelArgs a) {
+  __shared__ double s_buf[NodeBuf<MODE>::n * BLOCK];
   __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];
   void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
+  // One batch per block and a grid sized for the whole launch (the queue length is only known on the
+  // device): blocks beyond the queue exit at once, and the hardware block scheduler balances the
+  // very unequal walkers of this bucket.
   const int n = *a.queue_count;
-  for (int base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {   // block-uniform trip count
-    const int i = base + threadIdx.x;
-    const bool have = i < n;
-    const int w = have ? a.queue[i] : 0;
-    double th[MP_MAX_NDIM];
-    for (int d = 0; d < a.ndim; ++d) th[d] = a.theta[(size_t)w * a.ndim + d];
-    eval_one<MODE, BLOCK, true>(a, have, w, th, s_buf, scratch);
-  }
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (blockIdx.x * BLOCK >= n) return;
+  const bool have = i < n;
+  const int w = have ? a.queue[i] : 0;
+  double th[MP_MAX_NDIM];
+  for (int d = 0; d < a.ndim; ++d) th[d] = a.theta[(size_t)w * a.ndim + d];
+  eval_one<MODE, BLOCK, true>(a, have, w, th, s_buf, scratch);
 }
 
 // ---- counter-based RNG: Philox4x32-10 (Salmon et al. 2011) -------------------
@@ -246,14 +253,13 @@ stretch_kernel(const __grid_constant__ StretchArgs s) {
 }
 
 template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK) stretch_stiff_kernel(const __grid_constant__ StretchArgs s) {
+__global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) stretch_stiff_kernel(const __grid_constant__ StretchArgs s) {
   __shared__ double s_buf[kNB * BLOCK];
   const int n = *s.k.queue_count;
-  for (int base = blockIdx.x * BLOCK; base < n; base += gridDim.x * BLOCK) {
-    const int i = base + threadIdx.x;
-    const bool have = i < n;
-    stretch_one<BLOCK, true>(s, have, have ? s.k.queue[i] : s.active[0], s_buf);
-  }
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (blockIdx.x * BLOCK >= n) return;
+  const bool have = i < n;
+  stretch_one<BLOCK, true>(s, have, have ? s.k.queue[i] : s.active[0], s_buf);
 }
 
 // ---- the coupled right-hand side, as ODEs()/odes() return it -----------------------
@@ -510,13 +516,8 @@ static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream
   return MP_OK;
 }
 
-// grid of the stiff-bucket launch: grid-stride over a queue whose length is only known on the
-// device; a few blocks per SM are enough to cover it (it exits at once when the queue is empty)
-static int stiff_grid(const mp_handle* h, int W, int block) {
-  const int full = (W + block - 1) / block;
-  const int cap = h->sm_count * 8;
-  return full < cap ? full : cap;
-}
+// grid of the stiff-bucket launch: one block per batch of the longest possible queue
+static int stiff_grid(const mp_handle*, int W, int block) { return (W + block - 1) / block; }
 
 template <int MODE>
 static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane = 0) {

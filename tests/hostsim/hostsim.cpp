@@ -24,6 +24,21 @@ static DataView view_of(const NodeProgram& np, double t_start) {
   return dv;
 }
 
+// The kernels' bucketing on the host: explicit pass first; a walker it defers as stiff is re-run
+// from the start by the implicit variant (eval_kernel -> queue -> eval_stiff_kernel).
+template <int MODE>
+static double evaluate_two_pass(const Spec& sp, const DataView& dv, const Walker& wk, double* buf, int& st, int& nr,
+                                double* out, double* state, const int* dat_orig) {
+  int st1 = st, nr1 = 0;
+  double r = evaluate_walker<MODE, 64, false>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr);
+  if (st1 & kWalkerDeferred) {
+    st1 = st; nr1 = 0;
+    r = evaluate_walker<MODE, 64, true>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr);
+  }
+  st = st1; nr = nr1;
+  return r;
+}
+
 extern "C" int hs_lnprob(const mp_model_spec* ms, const mp_prior_spec* pr, const double* grid, int G,
                          const double* t, const double* y, const double* yerr, int D,
                          const double* theta, int W, int ndim, double* lnp, int* status, int* nrhs,
@@ -45,7 +60,7 @@ extern "C" int hs_lnprob(const mp_model_spec* ms, const mp_prior_spec* pr, const
       unpack_theta(sp, th, ndim, pars, de, pe, fb);
       Walker wk;
       walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
-      double chi2 = evaluate_walker<kModeLnprob, 64, true>(sp, dv, wk, true, buf.data(), 1, st, nr, nullptr, nullptr, 1, nullptr, nullptr);
+      double chi2 = evaluate_two_pass<kModeLnprob>(sp, dv, wk, buf.data(), st, nr, nullptr, nullptr, nullptr);
       double ll = -0.5 * chi2;
       if (st & kWalkerIntegratorFail) ll = -INFINITY;
       else if (!std::isfinite(ll)) { st |= kWalkerNonfiniteLnlike; ll = -INFINITY; }
@@ -78,8 +93,8 @@ extern "C" int hs_curves(const mp_model_spec* ms, const double* grid, int G, con
     Walker wk;
     walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
     int st = 0, nr = 0;
-    evaluate_walker<kModeCurves, 64, true>(sp, dv, wk, true, buf.data(), 1, st, nr, out + (size_t)w * 3 * Gs,
-                                     state ? state + (size_t)w * 2 * Gs : nullptr, 1, nullptr, nullptr);
+    evaluate_two_pass<kModeCurves>(sp, dv, wk, buf.data(), st, nr, out + (size_t)w * 3 * Gs,
+                                   state ? state + (size_t)w * 2 * Gs : nullptr, nullptr);
     if (status) status[w] = st;
     if (nrhs) nrhs[w] = nr;
   }
@@ -117,16 +132,16 @@ extern "C" int hs_model_at(const mp_model_spec* ms, const double* grid, int G, c
     Walker wk;
     walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
     int st = 0, nr = 0;
-    evaluate_walker<kModeModelAtData, 64, true>(sp, dv, wk, true, buf.data(), 1, st, nr, out + (size_t)w * D, nullptr, 1,
-                                          np.order.data(), nullptr);
+    evaluate_two_pass<kModeModelAtData>(sp, dv, wk, buf.data(), st, nr, out + (size_t)w * D, nullptr, np.order.data());
     if (status) status[w] = st;
   }
   return 0;
 }
 
-// per-step trace of one walker (debug aid): rows of (t, h, omega, fastness-1, accepted, stiff, hJ)
+// per-step trace of one walker (debug aid): rows of (t, h, omega after the step, accepted, implicit)
 extern "C" int hs_trace(const mp_model_spec* ms, const double* grid, int G, const double* pars_in, double t_end,
-                        double* out, int max_rows) {
+                        int implicit, double* out, int max_rows) {
+  (void)G;
   Spec sp = make_spec(*ms);
   sp.unlog_mask = 0;
   double pars[6], de, pe, fb;
@@ -137,19 +152,12 @@ extern "C" int hs_trace(const mp_model_spec* ms, const double* grid, int G, cons
   in.n_rhs = 0;
   integrator_init(sp, wk, grid[0], t_end, in);
   int n = 0;
-  while (in.t < t_end && in.status == 0 && n < max_rows) {
+  while (in.t < t_end && in.status == 0 && n < max_rows && !(in.stiff && !implicit)) {
     const double t0 = in.t, h0 = in.h;
-    const int stiff = in.stiff;
-    bool acc;
-    if (stiff) { const double tb = in.t; in = radau_step(sp, wk, t_end, in); acc = in.t > tb; }
-    else acc = integrator_step(sp, wk, t_end, in);
-    DiscAt d = disc_at(wk, in.t);
-    double f, J;
-    spin_rhs_jac(sp, wk, d, in.omega, f, J);
-    const bool cap = d.rm * in.omega >= wk.kc;
-    const double fast = cap ? wk.Ccap / sqrt(in.omega) : d.wq * in.omega;
-    double* r = out + (size_t)n * 8;
-    r[0] = t0; r[1] = h0; r[2] = in.omega; r[3] = fast - 1.0; r[4] = acc; r[5] = stiff; r[6] = h0 * J; r[7] = cap;
+    if (implicit) radau_step(sp, wk, t_end, in);
+    else integrator_step(sp, wk, t_end, in);
+    double* r = out + (size_t)n * 5;
+    r[0] = t0; r[1] = h0; r[2] = in.omega; r[3] = in.t > t0; r[4] = implicit;
     ++n;
   }
   return n;
