@@ -248,6 +248,9 @@ struct Walker {
   double tvI;      // 1/(tvisc I) : ni = Mdisc * tvI
   // luminosity stage (its own alpha/cs7/k/n may differ from the RHS's)
   double l_inv_tv, l_A_rm, l_Cw, l_Ccap, l_kc;
+  double l_sqrtA;     // sqrt(l_A_rm): with qa = l_sqrtA M^(-1/7): Rm = qa^2, w = qa^3 omega / sqrt(GM)
+  double l_sGMkc;     // sqrt(GM l_kc)
+  double l_GM_kc;     // GM / l_kc
   double Ldip_coef;   // mu^2/(6 c^3)
   double dipeff, propeff, f_beam;
   double omega0;
@@ -397,6 +400,9 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
   w.l_Cw = w.l_A_rm * sqrt(w.l_A_rm) / sqrt(kGM);
   w.l_kc = sp.lum_k * kC;
   w.l_Ccap = w.l_kc * sqrt(w.l_kc) / sqrt(kGM);
+  w.l_sqrtA = sqrt(w.l_A_rm);
+  w.l_sGMkc = sqrt(kGM * w.l_kc);
+  w.l_GM_kc = kGM / w.l_kc;
   w.dipeff = dipeff;
   w.propeff = propeff;
   w.f_beam = f_beam;
@@ -408,9 +414,9 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
 // Disc mass at time t (closed form of funcs.py:126-129).
 MP_HD double disc_mass(const Walker& w, double t) {
   const double u = fma(t, w.inv_tv, w.eps);
-  const double S = disc_S(u);
-  const double E = exp(w.u0 - u);
-  return fma(w.K, S, w.C * E);
+  TableAt ta;
+  const double S = table_locate(u, ta) ? poly10p(ta.row, ta.s, ta.s * ta.s) : disc_S_outside(u, ta.e);
+  return fma(w.K, S, w.C * exp_c(w.u0 - u));
 }
 
 // Quantities of the RHS that depend on time only (through the disc mass).
@@ -481,20 +487,27 @@ MP_HD double spin_rhs(const Spec& sp, const Walker& w, const DiscAt& d, double o
 // Luminosity stage at one node (erg/s, not yet /1e50): funcs.py:175-229.
 struct Lum { double tot, prop, dip; };
 
+MP_HD double rsqrt_pos(double x);
+MP_HD double rcp_pos(double x);
+MP_HD double exp_small(double x);
+
+// Same mathematics as funcs.py:179-229 at one node, with the hot-loop elementary functions
+// (x^(-1/7) to 4e-16, tanh to 4e-16 absolute, Newton reciprocal / reciprocal square root).
 MP_HD Lum luminosity(const Spec& sp, const Walker& w, double M, double omega) {
-  const double q = pow_m17(M);
-  const double q2 = q * q;
+  const double qa = w.l_sqrtA * pow_m17_fast(M);               // NaN for M <= 0, as the reference's power
   const double mdot = M * w.l_inv_tv;
-  double rm = w.l_A_rm * q2;
-  double fast;
-  if (rm * omega >= w.l_kc) {       // Rm >= k*Rlc  (funcs.py:189-190)
-    rm = w.l_kc / omega;
-    fast = w.l_Ccap / sqrt(omega);
-  } else {
-    fast = w.l_Cw * q2 * q * omega;
-  }
+  const double rm_u = qa * qa;                                 // funcs.py:186-187
+  const double r = rsqrt_pos(omega);
+  const bool capped = rm_u * omega >= w.l_kc;                  // Rm >= k*Rlc  (funcs.py:189-190)
+  const double rm = capped ? w.l_kc * (r * r) : rm_u;
+  const double fast = capped ? w.l_Ccap * r : (rm_u * qa) * (sp.inv_sqrtGM * omega);
   const double om2 = omega * omega;
-  const double th = tanh(sp.lum_n * (fast - 1.0));
+  const double x = sp.lum_n * (fast - 1.0);
+  double th;                                                   // tanh(n (w - 1)), funcs.py:200
+  if (x > 19.1) th = 1.0;
+  else if (x < -19.1) th = -1.0;
+  else th = fma(-2.0, rcp_pos(exp_small(x + x) + 1.0), 1.0);
+  if (!(x == x)) th = x;
   const double eta2 = 0.5 * (1.0 + th);
   const double eta1 = 1.0 - eta2;
   const double mprop = eta2 * mdot, macc = eta1 * mdot;
@@ -502,13 +515,17 @@ MP_HD Lum luminosity(const Spec& sp, const Walker& w, double M, double omega) {
   if (om2 > sp.omega2_breakup_lum) {
     nacc = 0.0;
   } else {
-    const double lever = (rm >= kR) ? sqrt(kGM * rm) : sp.sqrt_GMR;
+    const double lev = capped ? w.l_sGMkc * r : sp.sqrtGM * qa;   // sqrt(GM Rm)
+    const double lever = (rm < kR) ? sp.sqrt_GMR : lev;
     nacc = lever * (macc - mprop);
   }
   double ldip = w.dipeff * (w.Ldip_coef * (om2 * om2));
   if (ldip <= 0.0 || !isfinite(ldip)) ldip = 0.0;                      // funcs.py:216-219
   double lprop = -1.0 * nacc * omega;
-  if (sp.lprop_binding_term) lprop -= (kGM / rm) * eta2 * mdot;        // funcs.py:222-223
+  if (sp.lprop_binding_term) {                                         // funcs.py:222-223
+    const double gm_rm = capped ? w.l_GM_kc * omega : kGM * rcp_pos(rm_u);
+    lprop -= gm_rm * eta2 * mdot;
+  }
   lprop *= w.propeff;
   if (lprop <= 0.0 || !isfinite(lprop)) lprop = 0.0;                   // funcs.py:224-227
   Lum L;
