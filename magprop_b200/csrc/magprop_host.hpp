@@ -38,6 +38,11 @@ inline Spec make_spec(const mp_model_spec& m) {
   s.sGMkc = std::sqrt(kGM * s.kc);
   s.sqrtGM = std::sqrt(kGM);
   s.inv_sqrtGM = 1.0 / s.sqrtGM;
+  s.sqrtGM2 = 2.0 * s.sqrtGM;
+  s.sqrt_GMR2 = 2.0 * s.sqrt_GMR;
+  s.sGMkc2 = 2.0 * s.sGMkc;
+  s.rhs_n2 = 2.0 * s.rhs_n;
+  s.y_breakup_rhs = 1.0 / s.omega2_breakup_rhs;
   s.lprop_binding_term = m.lprop_binding_term;
   s.unlog_mask = m.unlog_mask;
   s.rtol = (m.rtol > 0.0) ? m.rtol : 1.0e-10;

@@ -150,14 +150,15 @@ extern "C" int hs_trace(const mp_model_spec* ms, const double* grid, int G, cons
   walker_setup(sp, pars, de, pe, fb, grid[0], wk);
   Integrator in;
   in.n_rhs = 0;
-  integrator_init(sp, wk, grid[0], t_end, in);
+  if (implicit) integrator_init<false>(sp, wk, grid[0], t_end, in);
+  else integrator_init<true>(sp, wk, grid[0], t_end, in);   // explicit variant: state is omega^-2
   int n = 0;
   while (in.t < t_end && in.status == 0 && n < max_rows && !(in.stiff && !implicit)) {
     const double t0 = in.t, h0 = in.h;
     if (implicit) radau_step(sp, wk, t_end, in);
     else integrator_step(sp, wk, t_end, in);
     double* r = out + (size_t)n * 5;
-    r[0] = t0; r[1] = h0; r[2] = in.omega; r[3] = in.t > t0; r[4] = implicit;
+    r[0] = t0; r[1] = h0; r[2] = implicit ? in.omega : 1.0 / std::sqrt(in.omega); r[3] = in.t > t0; r[4] = implicit;
     ++n;
   }
   return n;
