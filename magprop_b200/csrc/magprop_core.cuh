@@ -88,10 +88,12 @@ struct DataView {
   int n_nodes;             // nodes the evaluation needs, ascending in time
   int n_data;
   const double* node_t;    // [n_nodes]
-  const double* dat_y;     // [n_data] sorted by time
-  const double* dat_yerr;  // [n_data]
+  // data sorted by time, pre-divided on the host so the chi-square loop has no division:
+  //   residual (y - mod/1e50)/yerr = dat_ys - mod * dat_c
+  const double* dat_ys;    // [n_data] y / yerr
+  const double* dat_c;     // [n_data] 1e-50 / yerr
   const double* dat_dx;    // [n_data] x - t_lo            (0 when x is a grid node)
-  const double* dat_Dx;    // [n_data] t_hi - t_lo         (1 when x is a grid node)
+  const double* dat_w;     // [n_data] (x - t_lo)/(t_hi - t_lo): interpolation weight of the upper node
   const int* dat_lo;       // [n_data] index into node_t of the lower bracketing node
   double t_start;          // grid[0]: where the initial conditions hold
 };
@@ -124,22 +126,30 @@ MP_HD double bitsd(int64_t i) {
 struct TableAt {
   const double* row;
   double s;
-  int e;   // binade of u
 };
 
-MP_HD bool table_locate(double u, TableAt& ta) {
-  const int64_t b = dbits(u);
-  const int e = (int)((b >> 52) & 0x7ff) - 1023;
-  ta.e = e;
-  if (b < 0 || e < MP_DISC_EMIN || e > MP_DISC_EMAX) return false;   // u <= 0, NaN/inf, out of range
-  const int sub = (int)((b >> (52 - MP_DISC_NSUB_LOG2)) & ((1 << MP_DISC_NSUB_LOG2) - 1));
-  ta.row = &mp_disc_table[((e - MP_DISC_EMIN) << MP_DISC_NSUB_LOG2) + sub][0];
-  // mantissa in [1,2) -> local coordinate
-  const double m = bitsd((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-  const double centre = 1.0 + (sub + 0.5) * (1.0 / (1 << MP_DISC_NSUB_LOG2));
-  ta.s = (m - centre) * (double)(2 << MP_DISC_NSUB_LOG2);
-  return true;
+MP_HD int dhi(double x) { return (int)(dbits(x) >> 32); }
+MP_HD double dfromhi(unsigned hi) { return bitsd((int64_t)((uint64_t)hi << 32)); }
+
+// Rows are laid out by (binade, sub-interval), i.e. by the top 11 + MP_DISC_NSUB_LOG2 bits of u, so
+// the row index is one shift and one subtraction of the high word.  The local coordinate is
+// (u - centre) * 2^(NSUB_LOG2 + 1 - e); the centre of the sub-interval and that power of two are
+// both assembled from the high word.  Always yields a loadable row (row 0 when u is outside the
+// table -- u <= 0, subnormal, NaN/inf included) so callers can evaluate unconditionally and patch
+// the rare outside case afterwards.
+MP_HD bool table_locate_safe(double u, TableAt& ta) {
+  const int hi = dhi(u);
+  const int sh = 20 - MP_DISC_NSUB_LOG2;
+  const unsigned idx = (unsigned)((hi >> sh) - ((1023 + MP_DISC_EMIN) << MP_DISC_NSUB_LOG2));
+  const bool in = idx < (unsigned)((MP_DISC_EMAX - MP_DISC_EMIN + 1) << MP_DISC_NSUB_LOG2);
+  ta.row = &mp_disc_table[in ? idx : 0u][0];
+  const unsigned uh = (unsigned)hi;
+  const double centre = dfromhi((uh & ~((1u << sh) - 1u)) | (1u << (sh - 1)));
+  const double scale = dfromhi(((unsigned)(2046 + MP_DISC_NSUB_LOG2 + 1) << 20) - (uh & 0x7ff00000u));
+  ta.s = (u - centre) * scale;
+  return in;
 }
+MP_HD bool table_locate(double u, TableAt& ta) { return table_locate_safe(u, ta); }
 
 // degree-10 polynomial, split into even/odd halves for ILP
 MP_HD double poly10(const double* c, double s) {
@@ -185,29 +195,14 @@ MP_HD double poly10p(const double* c, double s, double s2) {
   return fma(od, s, ev);
 }
 
-// table_locate that always yields a loadable row (row 0 when u is outside the table), so the
-// caller can evaluate unconditionally and patch the rare outside case afterwards.
-MP_HD bool table_locate_safe(double u, TableAt& ta) {
-  const int64_t b = dbits(u);
-  const int e = (int)((b >> 52) & 0x7ff) - 1023;
-  ta.e = e;
-  const bool in = (b > 0) && ((unsigned)(e - MP_DISC_EMIN) <= (unsigned)(MP_DISC_EMAX - MP_DISC_EMIN));
-  const int sub = (int)((b >> (52 - MP_DISC_NSUB_LOG2)) & ((1 << MP_DISC_NSUB_LOG2) - 1));
-  const int idx = in ? (((e - MP_DISC_EMIN) << MP_DISC_NSUB_LOG2) + sub) : 0;
-  ta.row = &mp_disc_table[idx][0];
-  const double m = bitsd((b & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
-  const double centre = 1.0 + (sub + 0.5) * (1.0 / (1 << MP_DISC_NSUB_LOG2));
-  ta.s = (m - centre) * (double)(2 << MP_DISC_NSUB_LOG2);
-  return in;
-}
-
 // S outside the table (rare): convergent series below 2^-10, asymptotic above 2^22.
 // Kept out of line so the hot stage loop stays small.
 #if defined(__CUDACC__)
 __device__ __host__ __noinline__
 #endif
-static double disc_S_outside(double u, int e) {
+static double disc_S_outside(double u) {
   if (!(u > 0.0) || !(u < 1.0e300)) return NAN;
+  const int e = ((dhi(u) >> 20) & 0x7ff) - 1023;
   if (e > MP_DISC_EMAX) {  // next term 16/u^3 < 3e-19
     const double iu = 1.0 / u;
     const double c = cbrt(iu);
@@ -227,7 +222,7 @@ static double disc_S_outside(double u, int e) {
 MP_HD double disc_S(double u) {
   TableAt ta;
   if (table_locate(u, ta)) return poly10(ta.row, ta.s);
-  return disc_S_outside(u, ta.e);
+  return disc_S_outside(u);
 }
 
 // ---- per-walker constants ---------------------------------------------------
@@ -250,6 +245,7 @@ struct Walker {
   double sqrtA;    // sqrt(A_rm)
   double KqA;      // Kq * sqrtA : late-phase qa = KqA * Q(u)
   double tvI;      // 1/(tvisc I) : ni = Mdisc * tvI
+  double KtvI;     // K/(tvisc I) : late-phase ni = KtvI * S(u)
   // luminosity stage (its own alpha/cs7/k/n may differ from the RHS's)
   double l_inv_tv, l_A_rm, l_Cw, l_Ccap, l_kc;
   double l_sqrtA;     // sqrt(l_A_rm): with qa = l_sqrtA M^(-1/7): Rm = qa^2, w = qa^3 omega / sqrt(GM)
@@ -342,6 +338,34 @@ MP_HD double pow_m17_fast(double x) {
   return ok ? res : NAN;
 }
 
+// x^(-1/7) from a single-precision seed (two MUFU operations, ~3e-7) and one third-order
+// correction y (1 + e/7 + 4 e^2/49), e = 1 - x y^7: remainder 0.06 e^3 ~ 3e-19.  A third of the
+// FP64 work of pow_m17_fast and none of its integer exponent arithmetic.  Arguments outside the
+// single-precision range (and x <= 0, NaN) take pow_m17_fast.
+MP_HD double pow_m17_seeded(double x) {
+#if defined(__CUDA_ARCH__) && !defined(MP_POW_CVT)
+  // double <-> float through the bit patterns (the F2F conversions have ~19 cycles of latency each,
+  // measured; the seed only needs the leading 24 bits, truncated) and the bare MUFU operations.
+  const long long xb = __double_as_longlong(x);
+  const unsigned hi = (unsigned)(xb >> 32), lo = (unsigned)xb;
+  if (!(hi - (897u << 20) < (253u << 20))) return pow_m17_fast(x);   // outside float range, x <= 0, NaN
+  const float xf = __uint_as_float(((hi - (896u << 20)) << 3) | (lo >> 29));
+  float lg, sf;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(lg * (-1.0f / 7.0f)));
+  const unsigned fb = __float_as_uint(sf);
+  const double y = __hiloint2double((int)((fb >> 3) + (896u << 20)), (int)(fb << 29));
+#else
+  const float xf = (float)x;
+  const float sf = exp2f(log2f(xf) * (-1.0f / 7.0f));
+  if (!(xf > 1.0e-36f && xf < 1.0e37f)) return pow_m17_fast(x);
+  const double y = (double)sf;
+#endif
+  const double y2 = y * y, y4 = y2 * y2;
+  const double e = fma(-x, (y4 * y2) * y, 1.0);
+  return fma(y * e, fma(e, 4.0 / 49.0, 1.0 / 7.0), y);
+}
+
 MP_HD double rcp_fast(double x) {
 #if defined(__CUDA_ARCH__)
   return __drcp_rn(x);
@@ -395,6 +419,7 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
   w.sqrtA = sqrt(w.A_rm);
   w.KqA = w.Kq * w.sqrtA;
   w.tvI = w.inv_tv * sp.inv_inertia;
+  w.KtvI = w.K * w.tvI;
   w.sGMkc = sqrt(kGM * w.kc);
   w.Ldip_coef = (mu * mu) / (6.0 * (kC * kC * kC));
   w.Cdip_I = w.Ldip_coef * sp.inv_inertia;
@@ -420,7 +445,8 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
 MP_HD double disc_mass(const Walker& w, double t) {
   const double u = fma(t, w.inv_tv, w.eps);
   TableAt ta;
-  const double S = table_locate(u, ta) ? poly10p(ta.row, ta.s, ta.s * ta.s) : disc_S_outside(u, ta.e);
+  const double S = table_locate(u, ta) ? poly10p(ta.row, ta.s, ta.s * ta.s) : disc_S_outside(u);
+  if (u >= w.u_late) return w.K * S;            // transient below 1e-16 of K S
   return fma(w.K, S, w.C * exp_c(w.u0 - u));
 }
 
@@ -444,7 +470,7 @@ MP_HD DiscAt disc_at(const Walker& w, double t) {
     M = w.K * S;
     q = w.Kq * Q;
   } else {
-    const double S = in ? poly10(ta.row, ta.s) : disc_S_outside(u, ta.e);
+    const double S = in ? poly10(ta.row, ta.s) : disc_S_outside(u);
     const double E = exp_c(w.u0 - u);
     M = fma(w.K, S, w.C * E);
     q = pow_m17_fast(M);
@@ -499,7 +525,7 @@ MP_HD double exp_small(double x);
 // Same mathematics as funcs.py:179-229 at one node, with the hot-loop elementary functions
 // (x^(-1/7) to 4e-16, tanh to 4e-16 absolute, Newton reciprocal / reciprocal square root).
 MP_HD Lum luminosity(const Spec& sp, const Walker& w, double M, double omega) {
-  const double qa = w.l_sqrtA * pow_m17_fast(M);               // NaN for M <= 0, as the reference's power
+  const double qa = w.l_sqrtA * pow_m17_seeded(M);             // NaN for M <= 0, as the reference's power
   const double mdot = M * w.l_inv_tv;
   const double rm_u = qa * qa;                                 // funcs.py:186-187
   const double r = rsqrt_pos(omega);
@@ -676,6 +702,9 @@ struct Integrator {
   // implicit variant only: f, df/domega and the disc quantities at (t, omega), carried from step to step
   double J0, d0_qa, d0_ni;
   int have0;
+  // explicit variant only: the disc-mass transient exp(u0 - u(t)) at the current time, carried from
+  // step to step (see disc_stages_dp5)
+  double E;
 };
 
 MP_HD double dense_eval(const Integrator& in, double tq) {
@@ -719,6 +748,7 @@ MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, doub
   in.stiff = 0;
   in.stiff_votes = 0;
   in.have0 = 0;
+  in.E = 1.0;                        // u(t_start) = u0
   in.J0 = in.d0_qa = in.d0_ni = 0.0;
   in.status = kWalkerOk;
   in.t0 = t_start; in.hs = 1.0;
@@ -924,7 +954,7 @@ MP_HD void disc_stages(const Walker& w, const double* ts, StageDisc* d) {
 #pragma unroll
       for (int s = 0; s < N; ++s) {
         TableAt tb;
-        if (!table_locate(u[s], tb)) S[s] = disc_S_outside(u[s], tb.e);
+        if (!table_locate(u[s], tb)) S[s] = disc_S_outside(u[s]);
       }
     }
 #pragma unroll
@@ -932,9 +962,57 @@ MP_HD void disc_stages(const Walker& w, const double* ts, StageDisc* d) {
       const double E = exp_c(w.u0 - u[s]);
       const double M = fma(w.K, S[s], w.C * E);
       d[s].ni = M * w.tvI;
-      d[s].qa = w.sqrtA * pow_m17_fast(M);
+      d[s].qa = w.sqrtA * pow_m17_seeded(M);
     }
   }
+}
+
+// The same for the five stage times of a Dormand-Prince step, t + (1/5, 3/10, 4/5, 8/9, 1) h.
+// Before the late phase the disc mass needs the transient exp(u0 - u) at every stage.  The stage
+// fractions are multiples of 1/90, so with a = exp(-h/(90 tvisc)) the five factors are a^18, a^27,
+// a^72, a^80, a^90: ONE exponential and ten multiplications per step instead of five exponentials,
+// applied to the transient carried from the previous step (E_t -> E_end = E_t a^90).  The carried
+// value drifts by ~1e-14 per step relative to itself (90 x the rounding of a), i.e. <= 2e-12 over
+// the early phase -- two orders below the step tolerance; the luminosity stage does not use it.
+MP_HD void disc_stages_dp5(const Walker& w, const double* ts, double Et, double dl, StageDisc* d, double& Eend) {
+  double u[5];
+  TableAt ta[5];
+  bool in_all = true;
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    u[s] = fma(ts[s], w.inv_tv, w.eps);
+    in_all = table_locate_safe(u[s], ta[s]) && in_all;
+  }
+  if (in_all && u[0] >= w.u_late) {
+    // late phase: S and Q = S^(-1/7) from the same table row -- no exp, no log
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      const double s2 = ta[s].s * ta[s].s;
+      const double S = poly10p(ta[s].row, ta[s].s, s2);
+      const double Q = poly10p(ta[s].row + MP_DISC_ROW, ta[s].s, s2);
+      d[s].ni = w.KtvI * S;
+      d[s].qa = w.KqA * Q;
+    }
+    Eend = 0.0;
+    return;
+  }
+  if (!in_all) {                                        // parameters far outside the prior box
+    disc_stages<5>(w, ts, d);
+    Eend = exp_c(w.u0 - u[4]);
+    return;
+  }
+  const double a = exp_small(fmax(dl * (-1.0 / 90.0), -40.0));
+  const double a2 = a * a, a4 = a2 * a2, a8 = a4 * a4, a9 = a8 * a;
+  const double a18 = a9 * a9, a27 = a18 * a9, a36 = a18 * a18, a72 = a36 * a36;
+  const double E[5] = {Et * a18, Et * a27, Et * a72, Et * (a72 * a8), Et * (a72 * a18)};
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const double S = poly10p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
+    const double M = fma(w.K, S, w.C * E[s]);
+    d[s].ni = M * w.tvI;
+    d[s].qa = w.sqrtA * pow_m17_seeded(M);
+  }
+  Eend = E[4];
 }
 
 MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
@@ -949,11 +1027,14 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   in.t0 = t;
   const double ts[5] = {fma(DP::c2(), h, t), fma(DP::c3(), h, t), fma(DP::c4(), h, t), fma(DP::c5(), h, t), tn};
   StageDisc d[5];
-  disc_stages<5>(w, ts, d);
+  double Eend;
+  disc_stages_dp5(w, ts, in.E, (tn - t) * w.inv_tv, d, Eend);
   // (One shared copy of the chain: inlining it after each disc block lets the compiler overlap the
   // two, but lanes of a warp that sit in different phases then run the chain twice -- measured
   // 4 % slower on uniform ensembles, 11 % on spread ones.)
-  return step_spin_chain(sp, w, in, t, y, h, tn, d);
+  const bool accepted = step_spin_chain(sp, w, in, t, y, h, tn, d);
+  if (accepted) in.E = Eend;
+  return accepted;
 }
 
 // ---- Radau IIA (order 5) for the stiff phases -------------------------------------
@@ -1319,15 +1400,13 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
           if (dx == 0.0) {
             mod = L.tot;                                   // datum sits on a grid node
           } else {
-            const double slope = (L.tot - Lprev) / ldg(dv.dat_Dx + idat);
-            mod = fma(slope, dx, Lprev);                   // np.interp: slope*(x-x_lo)+y_lo
+            mod = fma(L.tot - Lprev, ldg(dv.dat_w + idat), Lprev);   // np.interp: slope*(x-x_lo)+y_lo
           }
-          mod /= 1.0e50;
           if (MODE == kModeLnprob) {
-            const double r = (ldg(dv.dat_y + idat) - mod) / ldg(dv.dat_yerr + idat);
+            const double r = fma(-mod, ldg(dv.dat_c + idat), ldg(dv.dat_ys + idat));   // (y - mod/1e50)/yerr
             chi2 = fma(r, r, chi2);
           } else {
-            out[(dat_orig ? dat_orig[idat] : idat) * ostride] = mod;
+            out[(dat_orig ? dat_orig[idat] : idat) * ostride] = mod / 1.0e50;
           }
           ++idat;
         }

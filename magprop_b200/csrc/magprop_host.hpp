@@ -60,6 +60,7 @@ struct NodeProgram {
   std::vector<double> node_t;          // unique nodes, ascending
   std::vector<int> node_grid_index;    // their indices in the grid
   std::vector<double> y, yerr, dx, Dx; // data sorted by time
+  std::vector<double> ys, c, w;        // y/yerr, 1e-50/yerr, dx/Dx: what the kernel reads (no division there)
   std::vector<int> lo;                 // index into node_t
   std::vector<int> order;              // sorted position -> original index
 };
@@ -96,10 +97,14 @@ inline int build_node_program(const double* grid, int G, const double* t, const 
     np.lo.push_back(li);
     np.y.push_back(y[o]);
     np.yerr.push_back(yerr[o]);
+    np.ys.push_back(y[o] / yerr[o]);
+    np.c.push_back(1.0e-50 / yerr[o]);
     if (need_hi[s]) {
       np.dx.push_back(t[o] - grid[glo[s]]);
       np.Dx.push_back(grid[glo[s] + 1] - grid[glo[s]]);
+      np.w.push_back(np.dx.back() / np.Dx.back());
     } else {
+      np.w.push_back(0.0);
       np.dx.push_back(0.0);
       np.Dx.push_back(1.0);
     }

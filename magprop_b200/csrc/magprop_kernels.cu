@@ -352,7 +352,7 @@ struct mp_handle {
   int D = 0;
   NodeProgram np;
   DeviceNodes data_nodes;
-  double *d_y = nullptr, *d_yerr = nullptr, *d_dx = nullptr, *d_Dx = nullptr;
+  double *d_y = nullptr, *d_yerr = nullptr, *d_dx = nullptr, *d_Dx = nullptr;   // y/yerr, 1e-50/yerr, dx, dx/Dx (DataView)
   int *d_lo = nullptr, *d_orig = nullptr;
   // curve node sets per stride
   std::map<int, DeviceNodes> curve_nodes;
@@ -443,9 +443,9 @@ extern "C" int mp_create(const mp_model_spec* spec, const mp_prior_spec* prior, 
   h->D = D;
   h->np = np;
   h->data_nodes.n_nodes = (int)np.node_t.size();
-  if ((rc = upload(&h->data_nodes.node_t, np.node_t)) || (rc = upload(&h->d_y, np.y)) ||
-      (rc = upload(&h->d_yerr, np.yerr)) || (rc = upload(&h->d_dx, np.dx)) ||
-      (rc = upload(&h->d_Dx, np.Dx)) || (rc = upload(&h->d_lo, np.lo)) ||
+  if ((rc = upload(&h->data_nodes.node_t, np.node_t)) || (rc = upload(&h->d_y, np.ys)) ||
+      (rc = upload(&h->d_yerr, np.c)) || (rc = upload(&h->d_dx, np.dx)) ||
+      (rc = upload(&h->d_Dx, np.w)) || (rc = upload(&h->d_lo, np.lo)) ||
       (rc = upload(&h->d_orig, np.order))) {
     mp_destroy(h);
     return rc;
@@ -489,10 +489,10 @@ static int fill_args(mp_handle* h, KernelArgs& a, const DeviceNodes& nodes, bool
   a.dv.t_start = h->grid[0];
   if (with_data) {
     a.dv.n_data = h->D;
-    a.dv.dat_y = h->d_y;
-    a.dv.dat_yerr = h->d_yerr;
+    a.dv.dat_ys = h->d_y;
+    a.dv.dat_c = h->d_yerr;
     a.dv.dat_dx = h->d_dx;
-    a.dv.dat_Dx = h->d_Dx;
+    a.dv.dat_w = h->d_Dx;
     a.dv.dat_lo = h->d_lo;
     a.dat_orig = h->d_orig;
   }

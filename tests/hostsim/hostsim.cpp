@@ -15,10 +15,10 @@ static DataView view_of(const NodeProgram& np, double t_start) {
   dv.n_nodes = (int)np.node_t.size();
   dv.n_data = (int)np.y.size();
   dv.node_t = np.node_t.data();
-  dv.dat_y = np.y.data();
-  dv.dat_yerr = np.yerr.data();
+  dv.dat_ys = np.ys.data();
+  dv.dat_c = np.c.data();
   dv.dat_dx = np.dx.data();
-  dv.dat_Dx = np.Dx.data();
+  dv.dat_w = np.w.data();
   dv.dat_lo = np.lo.data();
   dv.t_start = t_start;
   return dv;

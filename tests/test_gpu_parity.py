@@ -247,9 +247,10 @@ def test_property_zero_chi2_and_beaming_linearity(built):
     p = np.array([3.0, 1.5, 2e-3, 400.0, 2.0, 5.0])
     lk0 = Likelihood(A.packaged_model_spec(), grid, t, np.ones_like(t), np.ones_like(t))
     model = lk0.model_at_data(p)[0]
-    # data == model  =>  chi2 == 0 exactly
+    # data == model  =>  chi2 == 0 to rounding: the kernel forms the residual as y/yerr - mod*(1e-50/yerr)
+    # (both quotients taken on the host), so each of the 60 residuals is a few ulp of y/yerr = 10
     lk = Likelihood(A.packaged_model_spec(), grid, t, model, 0.1 * model)
-    assert lk.lnprob(p) == 0.0
+    assert abs(lk.lnprob(p)) < 60 * (10 * 4e-16) ** 2
     # f_beam scales the luminosity linearly (7-parameter packaged dispatch)
     m3 = lk0.model_at_data(np.append(p, 3.0))[0]
     assert relerr(m3, 3.0 * model).max() < 1e-15

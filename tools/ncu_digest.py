@@ -25,6 +25,7 @@ def main():
         per = (int(args[1]) / 32.0) * float(args[2])          # warp-level RHS evaluations
     hot = int(sys.argv[sys.argv.index("--hot") + 1]) if "--hot" in sys.argv else 0
     out_csv = sys.argv[sys.argv.index("--csv") + 1] if "--csv" in sys.argv else None
+    out_json = sys.argv[sys.argv.index("--json") + 1] if "--json" in sys.argv else None
     raw = ncu_csv(rep, "raw")
     hdr, units, row = raw[0], raw[1], raw[2]
     get = lambda k: row[hdr.index(k)] if k in hdr else "n/a"
@@ -69,6 +70,18 @@ def main():
     print(f"FP64-pipe instructions (DFMA+DMUL+DADD+DSETP) {fp64} = {100.0 * fp64 / tot:.1f}%" + (f"  per warp-RHS {fp64 / per:.1f}" if per else ""))
     for op, n in by.most_common(24):
         print(f"  {op:10s} {n:12d} {100.0 * n / tot:5.1f}%" + (f"  per-RHS {n / per:6.2f}" if per else "") + f"  samples {100.0 * smp[op] / max(tots, 1):5.1f}%")
+    if out_json and per:
+        import json
+        val = {k: v for k, v, _ in lines}
+        dram = (float(val["dram__bytes_read.sum"]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[units[hdr.index("dram__bytes_read.sum")]]
+                + float(val["dram__bytes_write.sum"]) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[units[hdr.index("dram__bytes_write.sum")]])
+        with open(out_json, "w") as f:
+            json.dump({"source": f"{out_csv or rep} (ncu --set full, {args[1]} walkers x {args[2]} RHS evaluations)",
+                       "flop_per_rhs": round((2 * by["DFMA"] + by["DMUL"] + by["DADD"]) / per, 1),
+                       "fp64_inst_per_rhs": round(fp64 / per, 1),
+                       "fp64_pipe_active_pct": round(float(val["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]), 1),
+                       "issue_active_pct": round(float(val["smsp__issue_active.avg.pct_of_peak_sustained_active"]), 1),
+                       "warp_inst_per_rhs": round(tot / per, 1), "dram_bytes_per_launch": int(dram)}, f, indent=1)
     if hot:
         print("\nhottest SASS lines by stall samples")
         for s_, n, txt in sorted(rows, reverse=True)[:hot]:
