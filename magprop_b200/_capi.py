@@ -57,6 +57,14 @@ def packaged_model_spec(dipeff=0.05, propeff=0.4, f_beam=1.0, n=1.0, alpha=0.1, 
                      0.27, 0.0, 0, 0, rtol, max_steps, 0)
 
 
+def figure_model_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9, rtol=0.0, max_steps=0) -> ModelSpec:
+    """The model the paper-figure scripts inline (code/figure_1.py:13,65, figure_4.py:14,114-177):
+    I = 4/5 M R^2, (3 Mdisc/tvisc)^(-2/7), break-up test 0.27 in both stages, Lprop with the binding
+    term, unit efficiencies, physical (not log) parameters, n swept per figure (1/10/50)."""
+    return ModelSpec(4.0 / 5.0, 3.0, n, alpha, cs7, k, n, alpha, cs7, k, 1.0, 1.0, 1.0,
+                     0.27, 0.27, 1, 0, rtol, max_steps, 0)
+
+
 def prior_spec(lower=None, upper=None) -> PriorSpec:
     p = PriorSpec()
     if lower is None:

@@ -93,6 +93,14 @@ def script_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9, dipeff=1.0, propeff=1.0,
                      dipeff, propeff, f_beam, 0.27, 0.27, True, 0.0, 6.0, 2)
 
 
+def figure_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9) -> ModelSpec:
+    """The copy of the model inlined in the paper-figure scripts: code/figure_4.py:14 (I = 4/5 M R^2),
+    :139-140 (3*Mdisc), :158-166 (0.27), :173 (binding term); figure_1.py:126 sweeps n."""
+    return ModelSpec("figure", 4.0 / 5.0, 3.0, n, alpha, cs7, k, n, alpha, cs7, k,
+                     1.0, 1.0, 1.0, 0.27, 0.27, True, 0.0, 6.0, 6,
+                     mdot_sum_prop_first=True)    # figure_1.py:88: Mdotfb - Mdotprop - Mdotacc
+
+
 def packaged_spec(GRBtype=None, dipeff=0.05, propeff=0.4, f_beam=1.0, n=1.0,
                   alpha=0.1, cs7=1.0, k=0.9) -> ModelSpec:
     """model_lc: magnetar/funcs.py:105-220 (RHS always sees odes' own defaults)."""
