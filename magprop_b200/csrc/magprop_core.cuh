@@ -338,6 +338,12 @@ MP_HD double pow_m17_fast(double x) {
   return ok ? res : NAN;
 }
 
+// pow_m17_fast out of line, for the rare arguments the seeded form below hands over.
+#if defined(__CUDACC__)
+__device__ __host__ __noinline__
+#endif
+static double pow_m17_cold(double x) { return pow_m17_fast(x); }
+
 // x^(-1/7) from a single-precision seed (two MUFU operations, ~3e-7) and one third-order
 // correction y (1 + e/7 + 4 e^2/49), e = 1 - x y^7: remainder 0.06 e^3 ~ 3e-19.  A third of the
 // FP64 work of pow_m17_fast and none of its integer exponent arithmetic.  Arguments outside the
@@ -348,7 +354,7 @@ MP_HD double pow_m17_seeded(double x) {
   // measured; the seed only needs the leading 24 bits, truncated) and the bare MUFU operations.
   const long long xb = __double_as_longlong(x);
   const unsigned hi = (unsigned)(xb >> 32), lo = (unsigned)xb;
-  if (!(hi - (897u << 20) < (253u << 20))) return pow_m17_fast(x);   // outside float range, x <= 0, NaN
+  if (!(hi - (897u << 20) < (253u << 20))) return pow_m17_cold(x);   // outside float range, x <= 0, NaN
   const float xf = __uint_as_float(((hi - (896u << 20)) << 3) | (lo >> 29));
   float lg, sf;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
@@ -358,7 +364,7 @@ MP_HD double pow_m17_seeded(double x) {
 #else
   const float xf = (float)x;
   const float sf = exp2f(log2f(xf) * (-1.0f / 7.0f));
-  if (!(xf > 1.0e-36f && xf < 1.0e37f)) return pow_m17_fast(x);
+  if (!(xf > 1.0e-36f && xf < 1.0e37f)) return pow_m17_cold(x);
   const double y = (double)sf;
 #endif
   const double y2 = y * y, y4 = y2 * y2;
@@ -1379,7 +1385,7 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
         om = (tn == dv.t_start) ? w.omega0 : NAN;
       } else {
         M = disc_mass(w, tn);
-        om = STIFF ? v : 1.0 / sqrt(v);
+        om = STIFF ? v : rsqrt_pos(v);       // ~1 ulp; NaN for a failed walker's NaN
       }
       const Lum L = luminosity(sp, w, M, om);
       if (MODE == kModeCurves) {
