@@ -80,6 +80,7 @@ struct Spec {
   int unlog_mask;
   double rtol;
   double rtol_stiff;           // tolerance of the Radau error estimate
+  double rtol_y;               // explicit variant: tolerance on y = omega^-2 (see make_spec)
   int max_steps;
 };
 
@@ -666,7 +667,10 @@ MP_HD double spin_f(const Spec& sp, const Walker& w, const StageDisc& d, double 
 // with omega = y^(-1/2) (one reciprocal square root -- the omega form needs one as well, for the
 // capped branch).  Same mathematics as spin_f / funcs.py:105-140.  The capped branch is a real
 // branch: it costs a second reciprocal square root, and the lanes of a warp mostly agree on it.
-MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double y, unsigned& side) {
+// `regime` (out): bit 0 = Alfven radius capped at k*Rlc, bit 1 = lever arm at its floor sqrt(GM R).  The
+// right-hand side is continuous but kinked where either bit flips; the step uses the bits of its two
+// end points to land on such a kink instead of stepping across it (see locate_kink).
+MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double y, unsigned& side, unsigned& regime) {
   const double om = rsqrt_pos(y);                              // omega
   const double iom = y * om;                                   // 1/omega
   const double rm = d.qa * d.qa;                               // uncapped Alfven radius
@@ -675,10 +679,14 @@ MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double 
   if (rm >= rcap) {                                            // Rm >= k*Rlc (funcs.py:109-110)
     const double r = rsqrt_pos(om);
     fast = sp.Ccap * r;
-    lever2 = (rcap >= kR) ? sp.sGMkc2 * r : sp.sqrt_GMR2;
+    const bool floor_ = !(rcap >= kR);
+    lever2 = floor_ ? sp.sqrt_GMR2 : sp.sGMkc2 * r;
+    regime = floor_ ? 3u : 1u;
   } else {                                                     // (also taken by a NaN qa, which then reaches the result)
     fast = (rm * d.qa) * (sp.inv_sqrtGM * om);
-    lever2 = (rm < kR) ? sp.sqrt_GMR2 : sp.sqrtGM2 * d.qa;     // funcs.py:135-138
+    const bool floor_ = rm < kR;
+    lever2 = floor_ ? sp.sqrt_GMR2 : sp.sqrtGM2 * d.qa;        // funcs.py:135-138
+    regime = floor_ ? 2u : 0u;
   }
   // tanh(n (w - 1)) to 4e-16 absolute; beyond |2x| = 38.2 it is +-1 to the last bit
   const double x2 = fma(sp.rhs_n2, fast, -sp.rhs_n2);
@@ -690,6 +698,11 @@ MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double 
   side |= above ? 2u : 1u;
   th = above ? 0.0 : th;
   return fma((lever2 * d.ni) * (y * iom), th, w.Cdip_I2);
+}
+
+MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double y, unsigned& side) {
+  unsigned regime;
+  return spin_g(sp, w, d, y, side, regime);
 }
 
 // ---- Dormand-Prince 5(4) with dense output --------------------------------
@@ -711,6 +724,9 @@ struct Integrator {
   // explicit variant only: the disc-mass transient exp(u0 - u(t)) at the current time, carried from
   // step to step (see disc_stages_dp5)
   double E;
+  unsigned regime;               // bits 0-1: spin_g's regime bits at (t, state); bits 2-3: the regime beyond the
+                                 // kink the current attempt is aimed at; bits 4..: kinks landed on so far
+  double h_resume;               // step size in use when that kink was met (> 0: the attempt is a landing)
 };
 
 MP_HD double dense_eval(const Integrator& in, double tq) {
@@ -735,11 +751,13 @@ MP_HD void disc_stages(const Walker& w, const double* ts, StageDisc* d);
 #if defined(__CUDACC__)
 __device__ __host__ __noinline__
 #endif
-static double spin_g_cold(const Spec& sp, const Walker& w, double t, double y) {
+static double spin_g_cold(const Spec& sp, const Walker& w, double t, double y, unsigned* regime) {
   StageDisc d;
   disc_stages<1>(w, &t, &d);
-  unsigned side = 0u;
-  return spin_g(sp, w, d, y, side);
+  unsigned side = 0u, rg = 0u;
+  const double g = spin_g(sp, w, d, y, side, rg);
+  if (regime) *regime = rg;
+  return g;
 }
 
 // INVSQ: the state is y = omega^-2 (explicit variant), tolerance 2 rtol (d(omega)/omega = dy/(2y)).
@@ -755,19 +773,23 @@ MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, doub
   in.stiff_votes = 0;
   in.have0 = 0;
   in.E = 1.0;                        // u(t_start) = u0
+  in.regime = 0u;
+  in.h_resume = 0.0;
   in.J0 = in.d0_qa = in.d0_ni = 0.0;
   in.status = kWalkerOk;
   in.t0 = t_start; in.hs = 1.0;
   in.r1 = in.omega; in.r2 = in.r3 = in.r4 = in.r5 = 0.0;
-  in.k1 = INVSQ ? spin_g_cold(sp, w, t_start, in.omega) : spin_f_cold(sp, w, t_start, in.omega);
+  unsigned rg0 = 0u;
+  in.k1 = INVSQ ? spin_g_cold(sp, w, t_start, in.omega, &rg0) : spin_f_cold(sp, w, t_start, in.omega);
+  in.regime = rg0;
   // initial step (Hairer's hinit, order 5)
-  const double sk = (INVSQ ? 2.0 * sp.rtol : sp.rtol) * fabs(in.omega);
+  const double sk = (INVSQ ? sp.rtol_y : sp.rtol) * fabs(in.omega);
   const double dnf = fabs(in.k1) / sk, dny = fabs(in.omega) / sk;
   double h = (dnf <= 1e-10 || dny <= 1e-10) ? 1.0e-6 : 0.01 * (dny / dnf);
   const double span = t_end - t_start;
   h = fmin(h, span);
   const double y1 = fma(h, in.k1, in.omega);
-  const double f1 = INVSQ ? spin_g_cold(sp, w, t_start + h, y1) : spin_f_cold(sp, w, t_start + h, y1);
+  const double f1 = INVSQ ? spin_g_cold(sp, w, t_start + h, y1, nullptr) : spin_f_cold(sp, w, t_start + h, y1);
   const double der2 = fabs(f1 - in.k1) / sk / h;
   const double der12 = fmax(der2, dnf);
   const double h1 = (der12 <= 1e-15) ? fmax(1.0e-6, fabs(h) * 1.0e-3)
@@ -856,9 +878,52 @@ static bool breakup_sliding_block_y(const Spec& sp, const Walker& w, const Stage
   return spin_g(sp, w, d, yb * (1.0 + 2.0e-12), side) < 0.0;
 }
 
+// Kinks.  The right-hand side is C0 but not C1 where the Alfven radius reaches the light-cylinder cap
+// (funcs.py:109-110) and where the lever arm reaches its floor (funcs.py:135-138).  A step across such a
+// kink loses its order: the controller answers with a burst of rejections and tiny steps (4-6 rejections
+// per kink on the synthetic truths), and what error it lets through is the LARGEST contribution to the
+// global error (measured: landing on the kinks lowers the error in omega 5-40x at equal rtol).  So when
+// the regime bits of a trial step's two end points differ, the crossing is located -- regula falsi on
+// the margin of the bit that flipped, with the state interpolated linearly (omega moves by < 1e-3 over a
+// step here, the margin is dominated by the disc mass) -- and the step is retried to END on the kink.
+// Returns the fraction of the step at which the kink sits, or -1.
+#if defined(__CUDACC__)
+__device__ __host__ __noinline__
+#endif
+static double locate_kink(const Spec& sp, const Walker& w, double t, double h, double y, double ynew, unsigned r0,
+                          unsigned r1) {
+  const bool cap_event = ((r0 ^ r1) & 1u) != 0u;
+  const bool capped = (r0 & 1u) != 0u;            // used by the floor event only (cap bit equal at both ends)
+  // margin(theta) > 0 on the side where the bit is set
+  double a = 0.0, b = 1.0, fa = 0.0, fb = 0.0;
+  for (int it = -2; it < 12; ++it) {
+    double th;
+    if (it == -2) th = 0.0;
+    else if (it == -1) th = 1.0;
+    else th = (a * fb - b * fa) / (fb - fa);
+    const double tt = fma(th, h, t);
+    const double yy = fma(th, ynew - y, y);
+    StageDisc d;
+    disc_stages<1>(w, &tt, &d);
+    const double rm = d.qa * d.qa;
+    const double rcap = sp.kc * (yy * rsqrt_pos(yy));
+    double m;
+    if (cap_event) m = rm - rcap;
+    else m = capped ? (kR - rcap) : (kR - rm);
+    if (!(m == m)) return -1.0;
+    if (it == -2) { fa = m; continue; }
+    if (it == -1) { fb = m; if (!(fa * fb < 0.0)) return -1.0; continue; }
+    if ((m < 0.0) == (fa < 0.0)) { a = th; fa = m; fb *= 0.5; }      // Illinois
+    else { b = th; fb = m; fa *= 0.5; }
+    if (b - a < 1.0e-9 || m == 0.0) return th;
+  }
+  return 0.5 * (a + b);
+}
+
 // Second half of the block step: the six serial spin-equation stages, error control, dense output.
-MP_HD bool step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, const double t, const double y,
-                           const double h, const double tn, const StageDisc* d) {
+// Returns 1 accepted, 0 rejected, 2 a kink lies inside the trial (y_trial / regime_trial describe its end).
+MP_HD int step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, const double t, const double y,
+                          const double h, const double tn, const StageDisc* d, double& y_trial, unsigned& regime_trial) {
   // ---- spin chain
   const double k1 = in.k1;
   unsigned side = (y < sp.y_breakup_rhs) ? 2u : 1u;
@@ -873,11 +938,22 @@ MP_HD bool step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, cons
   const double y6 = fma(h, fma(DP::a65(), k5, fma(DP::a64(), k4, fma(DP::a63(), k3, fma(DP::a62(), k2, DP::a61() * k1)))), y);
   const double k6 = spin_g(sp, w, d[4], y6, side);
   const double ynew = fma(h, fma(DP::b6(), k6, fma(DP::b5(), k5, fma(DP::b4(), k4, fma(DP::b3(), k3, DP::b1() * k1)))), y);
-  const double k7 = spin_g(sp, w, d[4], ynew, side);
+  unsigned regime_end;
+  const double k7 = spin_g(sp, w, d[4], ynew, side, regime_end);
   in.n_rhs += 6;
+#ifndef MP_NO_EVENTS
+  if (regime_end != (in.regime & 3u) && in.regime < (8u << 4) && !(in.h_resume > 0.0)) {
+    // a kink lies inside this trial step: the caller locates it (none of the stage values are live
+    // there) and the trial is dropped
+    y_trial = ynew;
+    regime_trial = regime_end;
+    in.n_steps++;
+    return 2;
+  }
+#endif
   const double esum = fma(DP::e7(), k7, fma(DP::e6(), k6, fma(DP::e5(), k5, fma(DP::e4(), k4, fma(DP::e3(), k3, DP::e1() * k1)))));
   const double errv = h * esum;
-  const double sk = (2.0 * sp.rtol) * fmax(fabs(y), fabs(ynew));   // in y = omega^-2: d(omega)/omega = dy/(2y)
+  const double sk = sp.rtol_y * fmax(fabs(y), fabs(ynew));
   const double aerr = fabs(errv);
   const bool accept = aerr <= sk;                 // false for NaN
   float errf = (float)aerr / (float)sk;
@@ -902,10 +978,17 @@ MP_HD bool step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, cons
     in.t = tn;
     in.omega = ynew;
     in.k1 = k7;
+    // (a step that was aimed at a kink ends on it: from here on the far side's regime holds, whichever
+    // side of the kink rounding put the end point on)
+    in.regime = (in.regime & ~3u) | ((in.h_resume > 0.0) ? ((in.regime >> 2) & 3u) : regime_end);
 #ifndef MP_NO_SLIDING
     if (side == 3u && breakup_sliding_block_y(sp, w, d[4], y, ynew, true)) in.status = kWalkerIntegratorFail;
 #endif
     in.h = in.rejected ? fmin(hnew, h) : hnew;
+    if (in.h_resume > 0.0) {                      // this was the (short) step that landed on a kink:
+      in.h = fmax(in.h, in.h_resume);             // carry on with the step size in use before it
+      in.h_resume = 0.0;
+    }
     in.rejected = 0;
     in.n_steps++;
     // stiffness detection: see integrator_step_rolled
@@ -917,18 +1000,19 @@ MP_HD bool step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, cons
       in.stiff_votes = 0;
     }
 #endif
-    return true;
+    return 1;
   }
   // rejected
   const double hnew = h * (double)(1.0f / fminf(facc1, fac11 / safe));
   in.h = hnew;
+  in.h_resume = 0.0;                  // (a rejected landing attempt: the shorter retry no longer reaches the kink)
   in.rejected = 1;
   in.n_steps++;
 #ifndef MP_NO_SLIDING
   if (side == 3u && breakup_sliding_block_y(sp, w, d[4], y, ynew, false)) in.status = kWalkerIntegratorFail;
 #endif
   if (!(fabs(hnew) > 1.0e-14 * fabs(t)) || in.n_steps >= sp.max_steps) in.status = kWalkerIntegratorFail;
-  return false;
+  return 0;
 }
 
 // Disc quantities at N stage times, evaluated as one block of independent chains.
@@ -1038,9 +1122,24 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   // (One shared copy of the chain: inlining it after each disc block lets the compiler overlap the
   // two, but lanes of a warp that sit in different phases then run the chain twice -- measured
   // 4 % slower on uniform ensembles, 11 % on spread ones.)
-  const bool accepted = step_spin_chain(sp, w, in, t, y, h, tn, d);
-  if (accepted) in.E = Eend;
-  return accepted;
+  double y_trial;
+  unsigned regime_trial;
+  const int code = step_spin_chain(sp, w, in, t, y, h, tn, d, y_trial, regime_trial);
+  if (code == 1) in.E = Eend;
+  if (code == 2) {
+    // locate the kink and aim the next attempt at it; one within 1e-4 of either end of the trial is
+    // left alone (its effect is O(1e-8) of a full crossing): the attempt is repeated as one-sided
+    const double th = locate_kink(sp, w, t, h, y, y_trial, in.regime & 3u, regime_trial);
+    if (th > 1.0e-4 && th < 1.0 - 1.0e-4) {
+      in.h = th * h;
+      in.h_resume = h;
+      in.regime = ((in.regime & ~(3u << 2)) | (regime_trial << 2)) + (1u << 4);
+    } else {
+      in.h = h;
+      in.regime = (in.regime & ~3u) | regime_trial;
+    }
+  }
+  return code == 1;
 }
 
 // ---- Radau IIA (order 5) for the stiff phases -------------------------------------
