@@ -369,6 +369,38 @@ def extras(args, liks, data, dev, rank, world, torch, O, A):
     out["posterior_spread_0.05_W262144"] = timed(np.clip(truth + 0.05 * rng.randn(1 << 18, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER))
     out["prior_uniform_W65536"] = timed(rng.uniform(O.SCRIPT_LOWER, O.SCRIPT_UPPER, size=(1 << 16, 6)), reps=1)
 
+    # ---- configs[2] shape: 15 independent short-GRB fits (packaged model, "S" grid, the sample's points per
+    # burst), bursts dealt round-robin to the ranks, no communication.  Synthetic light curves on log-uniform
+    # time stamps (the k-corrected sample is not on the GPU box).
+    from magprop_b200.engine import Likelihood as _L, time_grid as _tg
+    d_per_grb = [253, 80, 33, 1944, 19, 8, 112, 36, 52, 214, 410, 240, 172, 151, 63]
+    g3 = np.random.RandomState(3)
+    p3 = np.array([2.0, 3.0, 3e-3, 300.0, 1.0, 5.0])
+    lo3 = np.array([1e-3, 0.69, 1e-5, 50.0, 0.1, 1e-5]); hi3 = np.array([10.0, 10.0, 1e-1, 2000.0, 1000.0, 50.0])
+    W3, ms3, n3 = 32768, 0.0, 0
+    for i, D in enumerate(d_per_grb):
+        t3 = np.sort(10 ** g3.uniform(np.log10(0.011), np.log10(9e5), D))
+        th3 = p3 * (1 + 1e-3 * g3.randn(W3, 6))
+        if i % world != rank:
+            continue
+        l0 = _L(A.packaged_model_spec(), _tg("S"), t3, np.ones(D), np.ones(D), device=dev.index)
+        y3 = l0.model_at_data(p3)[0]; l0.close()
+        l3 = _L(A.packaged_model_spec(), _tg("S"), t3, y3, 0.25 * y3, lo3, hi3, device=dev.index)
+        d_t = torch.from_numpy(th3).to(dev); d_l = torch.empty(W3, dtype=torch.float64, device=dev)
+        for _ in range(2):
+            l3.lnprob_device(d_t.data_ptr(), W3, 6, d_l.data_ptr(), 0, 0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            l3.lnprob_device(d_t.data_ptr(), W3, 6, d_l.data_ptr(), 0, 0)
+        e1.record(); torch.cuda.synchronize()
+        ms3 += e0.elapsed_time(e1) / 3; n3 += W3
+        l3.close()
+    out["config3_sgrb_shapes_this_rank"] = {"bursts": n3 // W3, "walkers_per_burst": W3, "ms": ms3,
+                                            "evals_per_s": n3 / ms3 * 1e3 if ms3 else None,
+                                            "points_per_burst": d_per_grb, "model": "packaged, S grid"}
+
     # ---- fused on-device stretch move (one launch per half-step) -------------------------------
     from magprop_b200.sampler import DeviceEnsemble
     import torch.distributed as dist

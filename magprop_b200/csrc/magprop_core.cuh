@@ -77,6 +77,7 @@ struct Spec {
   // break-up boundary in y
   double sqrtGM2, sqrt_GMR2, sGMkc2, rhs_n2, y_breakup_rhs;
   int lprop_binding_term;
+  int lum_dipole_only;         // the luminosity stage's Lprop is identically 0 (see make_spec): only Ldip is evaluated
   int unlog_mask;
   double rtol;
   double rtol_stiff;           // tolerance of the Radau error estimate
@@ -532,6 +533,19 @@ MP_HD double exp_small(double x);
 // Same mathematics as funcs.py:179-229 at one node, with the hot-loop elementary functions
 // (x^(-1/7) to 4e-16, tanh to 4e-16 absolute, Newton reciprocal / reciprocal square root).
 MP_HD Lum luminosity(const Spec& sp, const Walker& w, double M, double omega) {
+  if (sp.lum_dipole_only) {
+    // packaged variant (magnetar/funcs.py:193,206): rot_param > 0.0 switches N_acc off at every node and
+    // Lprop = propeff*(-N_acc*omega) has no other term, so Lprop = 0 whatever the disc does (a NaN falls
+    // to the isfinite clamp, :207-208) and the light curve is the dipole term alone
+    const double o2 = omega * omega;
+    double ld = w.dipeff * (w.Ldip_coef * (o2 * o2));
+    if (ld <= 0.0 || !isfinite(ld)) ld = 0.0;
+    Lum L0;
+    L0.dip = ld;
+    L0.prop = 0.0;
+    L0.tot = w.f_beam * (ld + 0.0);
+    return L0;
+  }
   const double qa = w.l_sqrtA * pow_m17_seeded(M);             // NaN for M <= 0, as the reference's power
   const double mdot = M * w.l_inv_tv;
   const double rm_u = qa * qa;                                 // funcs.py:186-187
@@ -1458,7 +1472,8 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
           const double tn = ldg(dv.node_t + j);
           const double v = buf[lane * bstride + (src - lane)];         // column of lane `src`, row `lane`
           const double om = sw->bad ? ((tn == dv.t_start) ? sw->omega0 : NAN) : (STIFF ? v : 1.0 / sqrt(v));
-          const double M = sw->bad ? ((tn == dv.t_start) ? sw->M_init : NAN) : disc_mass(*sw, tn);
+          const double M = sw->bad ? ((tn == dv.t_start) ? sw->M_init : NAN)
+                                   : ((sp.lum_dipole_only && !so) ? 0.0 : disc_mass(*sw, tn));
           const Lum L = luminosity(sp, *sw, M, om);
           o[j] = L.tot / 1.0e50;
           o[Nn + j] = L.prop / 1.0e50;
@@ -1483,7 +1498,7 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
         M = (tn == dv.t_start) ? w.M_init : NAN;
         om = (tn == dv.t_start) ? w.omega0 : NAN;
       } else {
-        M = disc_mass(w, tn);
+        M = (sp.lum_dipole_only && !(MODE == kModeCurves && state_out)) ? 0.0 : disc_mass(w, tn);
         om = STIFF ? v : rsqrt_pos(v);       // ~1 ulp; NaN for a failed walker's NaN
       }
       const Lum L = luminosity(sp, w, M, om);

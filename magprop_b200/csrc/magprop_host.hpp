@@ -44,6 +44,8 @@ inline Spec make_spec(const mp_model_spec& m) {
   s.rhs_n2 = 2.0 * s.rhs_n;
   s.y_breakup_rhs = 1.0 / s.omega2_breakup_rhs;
   s.lprop_binding_term = m.lprop_binding_term;
+  // rot_param > breakup_lum holds at every node when breakup_lum <= 0 (rot_param >= 0): N_acc = 0 there
+  s.lum_dipole_only = (m.breakup_lum <= 0.0 && !m.lprop_binding_term) ? 1 : 0;
   s.unlog_mask = m.unlog_mask;
   s.rtol = (m.rtol > 0.0) ? m.rtol : 1.0e-10;
   // The explicit variant integrates y = omega^-2, so d(omega)/omega = dy/(2y): 2 rtol on y is rtol on omega.
