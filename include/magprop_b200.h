@@ -65,7 +65,8 @@ typedef struct mp_model_spec {
   int32_t unlog_mask;      /* bit i set: theta[i] is log10 and is un-logged before the model (mcmc_eqns.py:17: bits 2..5) */
   double rtol;             /* relative tolerance of the spin integrator (0 => default 1e-10) */
   int32_t max_steps;       /* step budget per walker (0 => default 50000)                   */
-  int32_t reserved;
+  int32_t dipole_torque;   /* RHS dipole torque: 0 classical -mu^2 w^3/(6c^3) (funcs.py:119) | 1 Bucciantini et al. (2006),
+                              (-2/3)(mu^2 w^3/c^3)(Rlc/Rm)^3 (figure_3.py:142-143); the luminosity stage keeps the classical Ldip */
 } mp_model_spec;
 
 /* Top-hat prior: inclusive bounds, NaN rejects (mcmc_eqns.py:40-49,

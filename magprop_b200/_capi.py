@@ -32,7 +32,7 @@ class ModelSpec(C.Structure):
         ("dipeff", C.c_double), ("propeff", C.c_double), ("f_beam", C.c_double),
         ("breakup_rhs", C.c_double), ("breakup_lum", C.c_double),
         ("lprop_binding_term", C.c_int32), ("unlog_mask", C.c_int32),
-        ("rtol", C.c_double), ("max_steps", C.c_int32), ("reserved", C.c_int32),
+        ("rtol", C.c_double), ("max_steps", C.c_int32), ("dipole_torque", C.c_int32),
     ]
 
 
@@ -57,12 +57,13 @@ def packaged_model_spec(dipeff=0.05, propeff=0.4, f_beam=1.0, n=1.0, alpha=0.1, 
                      0.27, 0.0, 0, 0, rtol, max_steps, 0)
 
 
-def figure_model_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9, rtol=0.0, max_steps=0) -> ModelSpec:
+def figure_model_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9, rtol=0.0, max_steps=0, bucciantini=False) -> ModelSpec:
     """The model the paper-figure scripts inline (code/figure_1.py:13,65, figure_4.py:14,114-177):
     I = 4/5 M R^2, (3 Mdisc/tvisc)^(-2/7), break-up test 0.27 in both stages, Lprop with the binding
-    term, unit efficiencies, physical (not log) parameters, n swept per figure (1/10/50)."""
+    term, unit efficiencies, physical (not log) parameters, n swept per figure (1/10/50).
+    ``bucciantini=True``: the RHS uses the dipole torque of Bucciantini et al. (2006) as figure_3.py:105-164 does."""
     return ModelSpec(4.0 / 5.0, 3.0, n, alpha, cs7, k, n, alpha, cs7, k, 1.0, 1.0, 1.0,
-                     0.27, 0.27, 1, 0, rtol, max_steps, 0)
+                     0.27, 0.27, 1, 0, rtol, max_steps, 1 if bucciantini else 0)
 
 
 def prior_spec(lower=None, upper=None) -> PriorSpec:

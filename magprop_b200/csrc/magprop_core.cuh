@@ -77,6 +77,8 @@ struct Spec {
   // break-up boundary in y
   double sqrtGM2, sqrt_GMR2, sGMkc2, rhs_n2, y_breakup_rhs;
   int lprop_binding_term;
+  int bucciantini;             // RHS dipole torque of Bucciantini et al. 2006 (figure_3.py:142-143): classical x 4 (Rlc/Rm)^3
+  double bucc_cap;             // 4/k^3: that factor where Rm is capped at k*Rlc
   int lum_dipole_only;         // the luminosity stage's Lprop is identically 0 (see make_spec): only Ldip is evaluated
   int unlog_mask;
   double rtol;
@@ -520,7 +522,12 @@ MP_HD double spin_rhs(const Spec& sp, const Walker& w, const DiscAt& d, double o
     const double th = tanh_abs(sp.rhs_n * (fast - 1.0));
     nacc = -lever * d.mdot * th;
   }
-  return fma(-w.Cdip_I * om2, omega, nacc * sp.inv_inertia);
+  double cdip = w.Cdip_I;
+  if (sp.bucciantini) {
+    const double q = kC / (omega * d.rm);                       // Rlc / Rm (uncapped)
+    cdip *= (d.rm * omega >= w.kc) ? sp.bucc_cap : 4.0 * q * q * q;
+  }
+  return fma(-cdip * om2, omega, nacc * sp.inv_inertia);
 }
 
 // Luminosity stage at one node (erg/s, not yet /1e50): funcs.py:175-229.
@@ -669,7 +676,12 @@ MP_HD double spin_f(const Spec& sp, const Walker& w, const StageDisc& d, double 
   const bool above = om2 > sp.omega2_breakup_rhs;
   side |= above ? 2u : 1u;
   th = above ? 0.0 : th;                                       // funcs.py:131-132
-  return fma(-w.Cdip_I * om2, omega, -(lever * d.ni) * th);
+  double cdip = w.Cdip_I;
+  if (sp.bucciantini) {
+    const double q = kC / (omega * rm);
+    cdip *= capped ? sp.bucc_cap : 4.0 * q * q * q;
+  }
+  return fma(-cdip * om2, omega, -(lever * d.ni) * th);
 }
 
 // The explicit integrator does not integrate omega but y = omega^-2.  Pure dipole spin-down,
@@ -684,6 +696,9 @@ MP_HD double spin_f(const Spec& sp, const Walker& w, const StageDisc& d, double 
 // `regime` (out): bit 0 = Alfven radius capped at k*Rlc, bit 1 = lever arm at its floor sqrt(GM R).  The
 // right-hand side is continuous but kinked where either bit flips; the step uses the bits of its two
 // end points to land on such a kink instead of stepping across it (see locate_kink).
+// (Classical dipole torque only: a spec with the Bucciantini torque is integrated by the implicit variant,
+// whose right-hand side carries the option -- the kernels route every walker there, so this hot function
+// pays nothing for a figure-script variant.)
 MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double y, unsigned& side, unsigned& regime) {
   const double om = rsqrt_pos(y);                              // omega
   const double iom = y * om;                                   // 1/omega
@@ -1204,8 +1219,14 @@ MP_HD void spin_fJ(const Spec& sp, const Walker& w, const StageDisc& d, double o
   const bool above = om2 > sp.omega2_breakup_rhs;
   side |= above ? 2u : 1u;
   if (above) { th = 0.0; sech2 = 0.0; }
-  f = fma(-w.Cdip_I * om2, omega, -(lever * d.ni) * th);
-  J = fma(-3.0 * w.Cdip_I, om2, -d.ni * fma(dlever, th, lever * sp.rhs_n * sech2 * dfast));
+  double cdip = w.Cdip_I, cdipJ = 3.0 * w.Cdip_I;
+  if (sp.bucciantini) {
+    const double q = kC / (omega * rm);
+    cdip *= capped ? sp.bucc_cap : 4.0 * q * q * q;             // uncapped: -4 C c^3 / Rm^3, no omega left
+    cdipJ = capped ? cdipJ * sp.bucc_cap : 0.0;
+  }
+  f = fma(-cdip * om2, omega, -(lever * d.ni) * th);
+  J = fma(-cdipJ, om2, -d.ni * fma(dlever, th, lever * sp.rhs_n * sech2 * dfast));
 }
 
 // One Radau IIA step.  The implicit variant of the kernel runs every step through here (walkers

@@ -43,6 +43,8 @@ inline Spec make_spec(const mp_model_spec& m) {
   s.sGMkc2 = 2.0 * s.sGMkc;
   s.rhs_n2 = 2.0 * s.rhs_n;
   s.y_breakup_rhs = 1.0 / s.omega2_breakup_rhs;
+  s.bucciantini = m.dipole_torque ? 1 : 0;
+  s.bucc_cap = 4.0 / (m.rhs_k * m.rhs_k * m.rhs_k);
   s.lprop_binding_term = m.lprop_binding_term;
   // rot_param > breakup_lum holds at every node when breakup_lum <= 0 (rot_param >= 0): N_acc = 0 there
   s.lum_dipole_only = (m.breakup_lum <= 0.0 && !m.lprop_binding_term) ? 1 : 0;

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) stretc
 
 // ---- the coupled right-hand side, as ODEs()/odes() return it -----------------------
 // funcs.py:75-142 / magnetar/funcs.py:33-101, operation order kept.
-__global__ void rhs_kernel(double inertia_factor, double mdot_factor, double breakup,
+__global__ void rhs_kernel(double inertia_factor, double mdot_factor, double breakup, int dipole_torque,
                            const double* __restrict__ y, const double* __restrict__ t,
                            const double* __restrict__ pars, double n, double alpha, double cs7, double k,
                            int W, double* __restrict__ dydt) {
@@ -287,7 +287,11 @@ __global__ void rhs_kernel(double inertia_factor, double mdot_factor, double bre
   const double x = kGM / (kR * (kC * kC));
   const double modW = 0.6 * kM * (kC * kC) * (x / (1.0 - 0.5 * x));
   const double rot_param = (0.5 * inertia * (omega * omega)) / modW;
-  const double Ndip = (-1.0 * (mu * mu) * (omega * omega * omega)) / (6.0 * (kC * kC * kC));
+  double Ndip = (-1.0 * (mu * mu) * (omega * omega * omega)) / (6.0 * (kC * kC * kC));
+  if (dipole_torque) {                                  // figure_3.py:142-143
+    const double q = Rlc / Rm;
+    Ndip = (-2.0 / 3.0) * (((mu * mu) * (omega * omega * omega)) / (kC * kC * kC)) * (q * q * q);
+  }
   const double eta2 = 0.5 * (1.0 + tanh(n * (w - 1.0)));
   const double eta1 = 1.0 - eta2;
   const double Mdotprop = eta2 * (Mdisc / tvisc);
@@ -519,11 +523,24 @@ static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream
 // grid of the stiff-bucket launch: one block per batch of the longest possible queue
 static int stiff_grid(const mp_handle*, int W, int block) { return (W + block - 1) / block; }
 
+// Every walker onto the stiff queue: a spec the explicit kernel does not implement (Bucciantini torque).
+__global__ void queue_all_kernel(int* queue, int* count, int W, const int* ids = nullptr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < W) queue[i] = ids ? ids[i] : i;
+  if (i == 0) *count = W;
+}
+
 template <int MODE>
 static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane = 0) {
   if (a.W == 0) return MP_OK;
   int rc = prepare_queue(h, a, a.W, stream, lane);
   if (rc) return rc;
+  if (a.sp.bucciantini) {
+    queue_all_kernel<<<(a.W + 255) / 256, 256, 0, stream>>>(a.queue, a.queue_count, a.W);
+    eval_stiff_kernel<MODE, 64><<<(a.W + 63) / 64, 64, 0, stream>>>(a);
+    MP_CUDA(cudaGetLastError());
+    return MP_OK;
+  }
   // small ensembles: 32-thread blocks spread the warps over more SMs
   if (a.W <= 148 * 64 * 4) {
     eval_kernel<MODE, 32><<<(a.W + 31) / 32, 32, 0, stream>>>(a);
@@ -720,7 +737,7 @@ extern "C" int mp_rhs_batch(const mp_model_spec* spec, const double* y, const do
   MP_CUDA(cudaMemcpy(d_y, y, (size_t)W * 2 * sizeof(double), cudaMemcpyHostToDevice));
   MP_CUDA(cudaMemcpy(d_t, t, (size_t)W * sizeof(double), cudaMemcpyHostToDevice));
   MP_CUDA(cudaMemcpy(d_p, pars, (size_t)W * 5 * sizeof(double), cudaMemcpyHostToDevice));
-  rhs_kernel<<<(W + 127) / 128, 128>>>(spec->inertia_factor, spec->mdot_factor, spec->breakup_rhs, d_y, d_t, d_p,
+  rhs_kernel<<<(W + 127) / 128, 128>>>(spec->inertia_factor, spec->mdot_factor, spec->breakup_rhs, spec->dipole_torque, d_y, d_t, d_p,
                                        knobs[0], knobs[1], knobs[2], knobs[3], W, d_o);
   MP_CUDA(cudaGetLastError());
   MP_CUDA(cudaMemcpy(dydt, d_o, (size_t)W * 2 * sizeof(double), cudaMemcpyDeviceToHost));
@@ -753,6 +770,12 @@ extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_ln
   s.accepted = d_accepted;
   if (n_active == 0) return MP_OK;
   if ((rc = prepare_queue(h, s.k, n_active, (cudaStream_t)stream))) return rc;
+  if (s.k.sp.bucciantini) {
+    queue_all_kernel<<<(n_active + 255) / 256, 256, 0, (cudaStream_t)stream>>>(s.k.queue, s.k.queue_count, n_active, d_active);
+    stretch_stiff_kernel<64><<<(n_active + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s);
+    MP_CUDA(cudaGetLastError());
+    return MP_OK;
+  }
   if (n_active <= 148 * 64 * 4) {
     stretch_kernel<32><<<(n_active + 31) / 32, 32, 0, (cudaStream_t)stream>>>(s);
     stretch_stiff_kernel<32><<<stiff_grid(h, n_active, 32), 32, 0, (cudaStream_t)stream>>>(s);

@@ -77,6 +77,7 @@ class ModelSpec:
     grid_hi: float
     unlog_from: int            # lnlike un-logs theta[unlog_from:6] (script: 2, mcmc_eqns.py:17; packaged: 6 = none)
     mdot_sum_prop_first: bool = False  # Mdotfb-Mdotprop-Mdotacc (magnetar/funcs.py:88) vs Mdotfb-Mdotacc-Mdotprop (funcs.py:129)
+    bucciantini: bool = False          # RHS dipole torque (-2/3)(mu^2 w^3/c^3)(Rlc/Rm)^3, figure_3.py:142-143
 
     @property
     def inertia(self) -> float:
@@ -93,11 +94,12 @@ def script_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9, dipeff=1.0, propeff=1.0,
                      dipeff, propeff, f_beam, 0.27, 0.27, True, 0.0, 6.0, 2)
 
 
-def figure_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9) -> ModelSpec:
+def figure_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9, bucciantini=False) -> ModelSpec:
     """The copy of the model inlined in the paper-figure scripts: code/figure_4.py:14 (I = 4/5 M R^2),
     :139-140 (3*Mdisc), :158-166 (0.27), :173 (binding term); figure_1.py:126 sweeps n."""
     return ModelSpec("figure", 4.0 / 5.0, 3.0, n, alpha, cs7, k, n, alpha, cs7, k,
                      1.0, 1.0, 1.0, 0.27, 0.27, True, 0.0, 6.0, 6,
+                     bucciantini=bucciantini,
                      mdot_sum_prop_first=True)    # figure_1.py:88: Mdotfb - Mdotprop - Mdotacc
 
 
@@ -131,7 +133,7 @@ MOD_W = _binding_energy()
 
 # --------------------------------------------------------------------------- a2
 def rhs(y, t, B, MdiscI, RdiscI, epsilon, delta, n, alpha, cs7, k,
-        inertia_factor=0.35, mdot_factor=3.0, breakup=0.27, prop_first=False):
+        inertia_factor=0.35, mdot_factor=3.0, breakup=0.27, prop_first=False, bucciantini=False):
     """Coupled RHS, funcs.py:75-142 / magnetar/funcs.py:33-101 (scalar form)."""
     Mdisc, omega = y
     inertia = inertia_factor * M_NS * R_NS ** 2.0
@@ -151,6 +153,8 @@ def rhs(y, t, B, MdiscI, RdiscI, epsilon, delta, n, alpha, cs7, k,
     rot_param = (0.5 * inertia * (omega ** 2.0)) / MOD_W
 
     Ndip = (-1.0 * (mu ** 2.0) * (omega ** 3.0)) / (6.0 * (C_LIGHT ** 3.0))
+    if bucciantini:                                            # figure_3.py:142-143
+        Ndip = ((-2.0 / 3.0) * (((mu ** 2.0) * (omega ** 3.0)) / (C_LIGHT ** 3.0)) * ((Rlc / Rm) ** 3.0))
     eta2 = 0.5 * (1.0 + np.tanh(n * (w - 1.0)))
     eta1 = 1.0 - eta2
     Mdotprop = eta2 * (Mdisc / tvisc)
@@ -176,7 +180,7 @@ def _rhs_for(spec: ModelSpec):
         return rhs(y, t, B, MdiscI, RdiscI, epsilon, delta, spec.rhs_n,
                    spec.rhs_alpha, spec.rhs_cs7, spec.rhs_k,
                    spec.inertia_factor, spec.mdot_factor, spec.breakup_rhs,
-                   spec.mdot_sum_prop_first)
+                   spec.mdot_sum_prop_first, spec.bucciantini)
     return f
 
 

@@ -30,7 +30,9 @@ template <int MODE>
 static double evaluate_two_pass(const Spec& sp, const DataView& dv, const Walker& wk, double* buf, int& st, int& nr,
                                 double* out, double* state, const int* dat_orig) {
   int st1 = st, nr1 = 0;
-  double r = evaluate_walker<MODE, 64, false>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr);
+  double r = 0.0;
+  if (sp.bucciantini) st1 |= kWalkerDeferred;      // launch_eval routes such a spec to the implicit variant
+  else r = evaluate_walker<MODE, 64, false>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr);
   if (st1 & kWalkerDeferred) {
     st1 = st; nr1 = 0;
     r = evaluate_walker<MODE, 64, true>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr);

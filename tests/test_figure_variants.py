@@ -25,6 +25,55 @@ def test_oracle_figure_rhs_is_the_figure_scripts_rhs():
             assert got[0] == want[0] and got[1] == want[1]
 
 
+def test_oracle_figure3_rhs_both_torques():
+    g = np.load(GOLD)
+    for row in g["figure_3"]:
+        y, t, pars, want, bucc = row[:2], row[2], row[3:8], row[9:11], bool(row[11])
+        got = O._rhs_for(O.figure_spec(n=10.0, bucciantini=bucc))(y, t, *pars)
+        assert got[0] == want[0] and got[1] == want[1]
+
+
+def test_core_bucciantini_curve_vs_oracle(hostsim):
+    """The per-walker core (host build) with the Bucciantini torque vs the oracle at figure_3.py's parameters."""
+    import ctypes as C
+    from magprop_b200.engine import time_grid
+    from test_host_logic import _hs_curves
+    p = np.array([[1.0, 5.0, 0.001, 1000.0, 0.1, 1.0]])                     # figure_3.py:173-178
+    out, state, st, _ = _hs_curves(hostsim, A.figure_model_spec(n=10.0, bucciantini=True), time_grid(None), p, stride=50)
+    assert st[0] == 0
+    tight = O.model(p[0], O.figure_spec(n=10.0, bucciantini=True), tight=True)
+    idx = np.arange(0, 10001, 50)
+    assert relerr(out[0, 0], tight[1][idx]).max() < 5e-7 and relerr(out[0, 2], tight[3][idx]).max() < 5e-7
+    plain = O.model(p[0], O.figure_spec(n=10.0), tight=True)
+    assert relerr(tight[1][idx], plain[1][idx]).max() > 0.1                  # the torque model matters
+
+
+@pytest.mark.gpu
+def test_figure3_rhs_on_device(built):
+    from magprop_b200.engine import rhs_batch
+    r = np.load(GOLD)["figure_3"]
+    for bucc in (False, True):
+        q = r[r[:, 11] == float(bucc)]
+        got = rhs_batch(A.figure_model_spec(n=10.0, bucciantini=bucc), q[:, :2], q[:, 2], q[:, 3:8], [10.0, 0.1, 1.0, 0.9])
+        assert relerr(got, q[:, 9:11]).max() < 1e-11
+
+
+@pytest.mark.gpu
+def test_figure3_bucciantini_curves_vs_oracle(built):
+    from magprop_b200.engine import Likelihood, time_grid
+    from test_gpu_parity import assert_curves_close
+    rng = np.random.RandomState(8)
+    pars = np.array([[1.0, 5.0, 0.001, 1000.0, 0.1, 1.0], [1.0, 5.0, 0.001, 100.0, 0.1, 1.0], [2.0, 2.0, 1e-4, 300.0, 1.0, 10.0]])
+    lk = Likelihood(A.figure_model_spec(n=10.0, bucciantini=True), time_grid(None))
+    out, st = lk.curves(pars, node_stride=25)
+    lk.close()
+    idx = np.arange(0, 10001, 25)
+    for i, p in enumerate(pars):
+        assert st[i] == 0
+        tight = O.model(p, O.figure_spec(n=10.0, bucciantini=True), tight=True)
+        assert_curves_close(out[i], tight[1:][:, idx])
+
+
 @pytest.mark.gpu
 def test_figure_rhs_on_device(built):
     from magprop_b200.engine import rhs_batch
