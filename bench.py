@@ -199,8 +199,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: one JSON line only
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "NONE"        # NCCL prints its version banner on stdout at both levels; stdout carries one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     data = load_datasets()
