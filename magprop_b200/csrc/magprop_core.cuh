@@ -912,41 +912,43 @@ static bool breakup_sliding_block_y(const Spec& sp, const Walker& w, const Stage
 // kink loses its order: the controller answers with a burst of rejections and tiny steps (4-6 rejections
 // per kink on the synthetic truths), and what error it lets through is the LARGEST contribution to the
 // global error (measured: landing on the kinks lowers the error in omega 5-40x at equal rtol).  So when
-// the regime bits of a trial step's two end points differ, the crossing is located -- regula falsi on
-// the margin of the bit that flipped, with the state interpolated linearly (omega moves by < 1e-3 over a
-// step here, the margin is dominated by the disc mass) -- and the step is retried to END on the kink.
+// the regime bits of a trial step's two end points differ, the crossing is located -- the margin of the
+// bit that flipped at the two ends, two regula-falsi refinements and a final secant estimate, with the
+// state interpolated linearly (omega moves by < 1e-3 over a step here; the margin is dominated by the
+// disc mass and is close to linear over a step, so this lands within ~1e-5 of the step) -- and the step
+// is retried to END on the kink.  Three disc-mass evaluations, no right-hand-side evaluations; kept this
+// small because in an ensemble that is spread out the lanes of a warp meet their kinks on different
+// trips and each call runs with one active lane.
 // Returns the fraction of the step at which the kink sits, or -1.
 #if defined(__CUDACC__)
 __device__ __host__ __noinline__
 #endif
-static double locate_kink(const Spec& sp, const Walker& w, double t, double h, double y, double ynew, unsigned r0,
-                          unsigned r1) {
+static double locate_kink(const Spec& sp, const Walker& w, double t, double h, double y, double ynew, double qa_end,
+                          unsigned r0, unsigned r1) {
   const bool cap_event = ((r0 ^ r1) & 1u) != 0u;
   const bool capped = (r0 & 1u) != 0u;            // used by the floor event only (cap bit equal at both ends)
-  // margin(theta) > 0 on the side where the bit is set
-  double a = 0.0, b = 1.0, fa = 0.0, fb = 0.0;
-  for (int it = -2; it < 12; ++it) {
-    double th;
-    if (it == -2) th = 0.0;
-    else if (it == -1) th = 1.0;
-    else th = (a * fb - b * fa) / (fb - fa);
-    const double tt = fma(th, h, t);
+  // margin(theta): changes sign where the bit flips
+  auto margin = [&](double th, double qa) {
     const double yy = fma(th, ynew - y, y);
-    StageDisc d;
-    disc_stages<1>(w, &tt, &d);
-    const double rm = d.qa * d.qa;
+    const double rm = qa * qa;
     const double rcap = sp.kc * (yy * rsqrt_pos(yy));
-    double m;
-    if (cap_event) m = rm - rcap;
-    else m = capped ? (kR - rcap) : (kR - rm);
+    return cap_event ? rm - rcap : (capped ? kR - rcap : kR - rm);
+  };
+  StageDisc d;
+  disc_stages<1>(w, &t, &d);
+  double a = 0.0, b = 1.0, fa = margin(0.0, d.qa), fb = margin(1.0, qa_end);
+  if (!(fa * fb < 0.0)) return -1.0;              // also NaN
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double th = (a * fb - b * fa) / (fb - fa);
+    const double tt = fma(th, h, t);
+    disc_stages<1>(w, &tt, &d);
+    const double m = margin(th, d.qa);
     if (!(m == m)) return -1.0;
-    if (it == -2) { fa = m; continue; }
-    if (it == -1) { fb = m; if (!(fa * fb < 0.0)) return -1.0; continue; }
-    if ((m < 0.0) == (fa < 0.0)) { a = th; fa = m; fb *= 0.5; }      // Illinois
-    else { b = th; fb = m; fa *= 0.5; }
-    if (b - a < 1.0e-9 || m == 0.0) return th;
+    if ((m < 0.0) == (fa < 0.0)) { a = th; fa = m; }
+    else { b = th; fb = m; }
   }
-  return 0.5 * (a + b);
+  return (a * fb - b * fa) / (fb - fa);
 }
 
 // Second half of the block step: the six serial spin-equation stages, error control, dense output.
@@ -1020,7 +1022,8 @@ MP_HD int step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, const
     }
     in.rejected = 0;
     in.n_steps++;
-    // stiffness detection: see integrator_step_rolled
+    // stiffness detection: |lambda| t > 30 (lambda from the last two stages, which share their time)
+    // while h << t, twelve accepted steps in a row -> the walker is deferred to the implicit variant
 #ifndef MP_NO_VOTES
     const double dy = fabs(ynew - y6);
     if (fabs(k7 - k6) * tn > 30.0 * dy && h < 0.02 * tn) {   // |lambda| t > 30 while h << t
@@ -1156,10 +1159,10 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   const int code = step_spin_chain(sp, w, in, t, y, h, tn, d, y_trial, regime_trial);
   if (code == 1) in.E = Eend;
   if (code == 2) {
-    // locate the kink and aim the next attempt at it; one within 1e-4 of either end of the trial is
-    // left alone (its effect is O(1e-8) of a full crossing): the attempt is repeated as one-sided
-    const double th = locate_kink(sp, w, t, h, y, y_trial, in.regime & 3u, regime_trial);
-    if (th > 1.0e-4 && th < 1.0 - 1.0e-4) {
+    // locate the kink and aim the next attempt at it; one within 1e-3 of either end of the trial is
+    // left alone (its effect is O(1e-6) of a full crossing): the attempt is repeated as one-sided
+    const double th = locate_kink(sp, w, t, h, y, y_trial, d[4].qa, in.regime & 3u, regime_trial);
+    if (th > 1.0e-3 && th < 1.0 - 1.0e-3) {
       in.h = th * h;
       in.h_resume = h;
       in.regime = ((in.regime & ~(3u << 2)) | (regime_trial << 2)) + (1u << 4);

@@ -240,6 +240,29 @@ def test_properties_one_million_walkers(built, golden):
     lk.close()
 
 
+def test_ten_million_walkers_config5_size(built, golden):
+    """BASELINE configs[4] size (1e7 walkers on Humped): 39 063 copies of one 256-walker ensemble spread
+    around the posterior.  Every copy must reproduce the first bit for bit (no dependence on block, lane
+    or chunk placement -- the host-pointer call splits the batch into wave-sized chunks on two streams),
+    and the kink-landing / stiff-bucket machinery must leave no walker without a result."""
+    g = golden["lnprob_script"]
+    lk = script_lik(g, "Humped")
+    rng = np.random.RandomState(11)
+    base = np.clip(O.SYNTH_TRUTHS_LOG["Humped"] + 0.05 * rng.randn(256, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER)
+    copies = 39063
+    theta = np.tile(base, (copies, 1))
+    assert theta.shape[0] >= 10 ** 7
+    lnp, status, nrhs = lk.lnprob(theta, return_info=True)
+    first = lnp[:256]
+    assert np.isfinite(first).all() and (status[:256] == 0).all()
+    assert (lnp.reshape(copies, 256) == first[None, :]).all()
+    assert (nrhs.reshape(copies, 256) == nrhs[None, :256]).all()
+    want = O.lnprob_batch(base[:4], g["Humped_x"], g["Humped_y"], g["Humped_yerr"], O.script_spec(),
+                          O.SCRIPT_LOWER, O.SCRIPT_UPPER, tight=True)
+    assert relerr(first[:4], want).max() < TOL_TIGHT
+    lk.close()
+
+
 def test_property_zero_chi2_and_beaming_linearity(built):
     grid = time_grid("S")
     rng = np.random.RandomState(4)

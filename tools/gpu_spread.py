@@ -1,4 +1,5 @@
-"""Time lnprob on a posterior-like spread (developer tool)."""
+"""Ball vs posterior-like spread vs prior-uniform ensembles on one dataset (developer tool): evaluations/s,
+RHS statistics and the per-warp imbalance (max lane / mean lane RHS count)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import numpy as np, torch
@@ -6,18 +7,22 @@ from magprop_b200 import _capi as A
 from magprop_b200.engine import Likelihood, time_grid
 from oracle import magprop_oracle as O
 g = np.load(os.path.join(ROOT, "tests/golden/lnprob_script.npz"))
-W = int(os.environ.get("W", 262144)); name = os.environ.get("DS", "Classic"); sig = float(os.environ.get("SIG", 0.05))
+name = os.environ.get("DS", "Classic"); W = int(os.environ.get("W", 1 << 18))
 lk = Likelihood(A.script_model_spec(), time_grid(None), g[f"{name}_x"], g[f"{name}_y"], g[f"{name}_yerr"], O.SCRIPT_LOWER, O.SCRIPT_UPPER)
-rng = np.random.RandomState(99)
-theta = np.clip(O.SYNTH_TRUTHS_LOG[name] + sig*rng.randn(W,6), O.SCRIPT_LOWER, O.SCRIPT_UPPER)
-if os.environ.get("SORT"):
-    theta = theta[np.lexsort((theta[:,4], theta[:,3]))]
-d_th = torch.from_numpy(theta).cuda(); d_lnp = torch.empty(W, dtype=torch.float64, device="cuda"); d_nr = torch.empty(W, dtype=torch.int32, device="cuda")
-for _ in range(3): lk.lnprob_device(d_th.data_ptr(), W, 6, d_lnp.data_ptr(), 0, d_nr.data_ptr())
-torch.cuda.synchronize()
-e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(5): lk.lnprob_device(d_th.data_ptr(), W, 6, d_lnp.data_ptr(), 0, d_nr.data_ptr())
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1)/5
-print("%s sig=%g W=%d: %.3f ms %.3e evals/s nrhs mean %.0f max %d stiff %d" % (name, sig, W, ms, W/ms*1e3, d_nr.float().mean().item(), d_nr.max().item(), lk.last_stiff_count()))
+rng = np.random.RandomState(5)
+truth = O.SYNTH_TRUTHS_LOG[name]
+cases = {"ball 1e-4": truth + 1e-4 * rng.randn(W, 6),
+         "spread 0.01": np.clip(truth + 0.01 * rng.randn(W, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER),
+         "spread 0.05": np.clip(truth + 0.05 * rng.randn(W, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER),
+         "spread 0.2": np.clip(truth + 0.2 * rng.randn(W, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER)}
+for label, th in cases.items():
+    d_th = torch.from_numpy(np.ascontiguousarray(th)).cuda(); d_l = torch.empty(W, dtype=torch.float64, device="cuda"); d_n = torch.empty(W, dtype=torch.int32, device="cuda")
+    for _ in range(2): lk.lnprob_device(d_th.data_ptr(), W, 6, d_l.data_ptr(), 0, d_n.data_ptr())
+    torch.cuda.synchronize()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5): lk.lnprob_device(d_th.data_ptr(), W, 6, d_l.data_ptr(), 0, d_n.data_ptr())
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    nr = d_n.cpu().numpy().reshape(-1, 32)
+    print(f"{label:12s} {ms:7.3f} ms  {W / ms * 1e3:.3e} evals/s  mean_rhs {nr.mean():.0f}  per-warp max {nr.max(1).mean():.0f}  stiff {lk.last_stiff_count()}")
