@@ -191,7 +191,8 @@ def run_ours(args):
     import torch.distributed as dist
     from magprop_b200 import _capi as A
     from magprop_b200.engine import Likelihood, time_grid, fp64_peak_tflops
-    from oracle import magprop_oracle as O   # truths / prior constants only (no compute)
+    from magprop_b200.synthetic.mcmc_eqns import lower as PRIOR_LOWER, upper as PRIOR_UPPER   # mcmc_eqns.py:40-41
+    from magprop_b200.synthetic.synth_mcmc import truths as TRUTHS_LOG                        # synth_mcmc.py:16-21
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,12 +207,12 @@ def run_ours(args):
     data = load_datasets()
     grid = time_grid(None)
     spec = A.script_model_spec()
-    liks = {n: Likelihood(spec, grid, *data[n], O.SCRIPT_LOWER, O.SCRIPT_UPPER, device=local) for n in DATASETS}
+    liks = {n: Likelihood(spec, grid, *data[n], PRIOR_LOWER, PRIOR_UPPER, device=local) for n in DATASETS}
     W = args.ensembles * args.nwalk
     rng = np.random.RandomState(20170613 + rank)
     host_theta, d_theta, d_lnp, d_nrhs = {}, {}, {}, {}
     for n in DATASETS:
-        th = O.SYNTH_TRUTHS_LOG[n] + 1e-4 * rng.randn(W, 6)
+        th = TRUTHS_LOG[n] + 1e-4 * rng.randn(W, 6)
         host_theta[n] = torch.from_numpy(th).pin_memory()
         d_theta[n] = host_theta[n].to(dev)
         d_lnp[n] = torch.empty(W, dtype=torch.float64, device=dev)
@@ -282,7 +283,7 @@ def run_ours(args):
 
     extra = {}
     if not args.no_extra:
-        extra = extras(args, liks, data, dev, rank, world, torch, O, A)
+        extra = extras(args, liks, data, dev, rank, world, torch, (TRUTHS_LOG, PRIOR_LOWER, PRIOR_UPPER), A)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -337,8 +338,9 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def extras(args, liks, data, dev, rank, world, torch, O, A):
+def extras(args, liks, data, dev, rank, world, torch, consts, A):
     """Secondary measurements (not the headline): other ensemble shapes."""
+    TRUTHS_LOG, PRIOR_LOWER, PRIOR_UPPER = consts
     out = {}
     rng = np.random.RandomState(99 + rank)
     lk = liks["Classic"]
@@ -362,12 +364,12 @@ def extras(args, liks, data, dev, rank, world, torch, O, A):
         return {"walkers": W, "ms": ms, "evals_per_s": W / ms * 1e3, "mean_rhs": float(d_n.double().mean().item()),
                 "max_rhs": int(d_n.max().item()), "stiff_bucket": lk.last_stiff_count()}
 
-    truth = O.SYNTH_TRUTHS_LOG[name]
+    truth = TRUTHS_LOG[name]
     out["config2_exact_half_step_128_walkers"] = timed(truth + 1e-4 * rng.randn(128, 6), reps=20)
     for W in (10 ** 2, 10 ** 4, 10 ** 6):
         out[f"ball_1e-4_W{W}"] = timed(truth + 1e-4 * rng.randn(W, 6))
-    out["posterior_spread_0.05_W262144"] = timed(np.clip(truth + 0.05 * rng.randn(1 << 18, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER))
-    out["prior_uniform_W65536"] = timed(rng.uniform(O.SCRIPT_LOWER, O.SCRIPT_UPPER, size=(1 << 16, 6)), reps=1)
+    out["posterior_spread_0.05_W262144"] = timed(np.clip(truth + 0.05 * rng.randn(1 << 18, 6), PRIOR_LOWER, PRIOR_UPPER))
+    out["prior_uniform_W65536"] = timed(rng.uniform(PRIOR_LOWER, PRIOR_UPPER, size=(1 << 16, 6)), reps=1)
 
     # ---- configs[2] shape: 15 independent short-GRB fits (packaged model, "S" grid, the sample's points per
     # burst), bursts dealt round-robin to the ranks, no communication.  Synthetic light curves on log-uniform

@@ -158,3 +158,32 @@ def test_core_model_at_data_S_grid(hostsim, golden):
                                A.ptr(out), A.ptr(st)) == 0
     assert st[0] == 0
     assert relerr(out[0], g["model_at_truth"]).max() < 1e-6
+
+
+def test_core_steps_land_on_the_cap_kink(hostsim):
+    """The explicit integrator ends a step on the time at which the Alfven radius reaches the light-cylinder
+    cap (funcs.py:109-110) instead of stepping across the kink, for each of the four synthetic truths."""
+    from scipy.optimize import brentq
+    grid = time_grid(None)
+    spec = A.script_model_spec(unlog=False)
+    for name, p in O.SYNTH_TRUTHS.items():
+        pars = np.ascontiguousarray(np.asarray(p, float))
+        out = np.zeros((4000, 5))
+        n = hostsim.hs_trace(C.byref(spec), A.ptr(grid), grid.size, A.ptr(pars), C.c_double(1e6), 0, A.ptr(out), 4000)
+        rows = out[:n]
+        acc = rows[rows[:, 3] > 0]
+        t_end, om_end = acc[:, 0] + acc[:, 1], acc[:, 2]
+        assert n < 140 and (n - len(acc)) <= 4                       # trial steps, discarded trials
+        # margin Rm - k*Rlc along the accepted solution (oracle formulas), its sign change and root
+        soln = O.integrate(pars, O.script_spec(), tight=True)[0]
+        Md, om = soln[:, 0], soln[:, 1]
+        B, P, MdiscI, RdiscI, eps, delta = pars
+        tvisc = RdiscI * 1e5 / (0.1 * 1.0 * 1e7)
+        mu = 1e15 * B * O.R_NS ** 3
+        Rm = mu ** (4 / 7) * O.GM ** (-1 / 7) * (3 * Md / tvisc) ** (-2 / 7)
+        margin = Rm - 0.9 * O.C_LIGHT / om
+        i = np.where(np.sign(margin[1:]) != np.sign(margin[:-1]))[0]
+        assert i.size == 1
+        j = i[0]
+        t_kink = grid[j] + (grid[j + 1] - grid[j]) * margin[j] / (margin[j] - margin[j + 1])
+        assert np.abs(t_end / t_kink - 1.0).min() < 1e-4, name      # (h/t ~ 0.1 here: a chance hit has probability ~1e-3)
