@@ -186,4 +186,6 @@ def test_core_steps_land_on_the_cap_kink(hostsim):
         assert i.size == 1
         j = i[0]
         t_kink = grid[j] + (grid[j + 1] - grid[j]) * margin[j] / (margin[j] - margin[j + 1])
-        assert np.abs(t_end / t_kink - 1.0).min() < 1e-4, name      # (h/t ~ 0.1 here: a chance hit has probability ~1e-3)
+        # the state is interpolated linearly when the kink is located, so the landing is good to ~1e-3 of the
+        # step (h/t ~ 0.1 here; a chance hit within 5e-4 of t has probability ~1e-2)
+        assert np.abs(t_end / t_kink - 1.0).min() < 5e-4, name
