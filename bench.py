@@ -369,7 +369,13 @@ def extras(args, liks, data, dev, rank, world, torch, consts, A):
     for W in (10 ** 2, 10 ** 4, 10 ** 6):
         out[f"ball_1e-4_W{W}"] = timed(truth + 1e-4 * rng.randn(W, 6))
     out["posterior_spread_0.05_W262144"] = timed(np.clip(truth + 0.05 * rng.randn(1 << 18, 6), PRIOR_LOWER, PRIOR_UPPER))
-    out["prior_uniform_W65536"] = timed(rng.uniform(PRIOR_LOWER, PRIOR_UPPER, size=(1 << 16, 6)), reps=1)
+    prior_draws = rng.uniform(PRIOR_LOWER, PRIOR_UPPER, size=(1 << 16, 6))
+    out["prior_uniform_W65536"] = timed(prior_draws, reps=1)
+    lk.set_bucketing(True)          # walkers ordered by a cost key on the device (mp_set_bucketing)
+    out["prior_uniform_W65536_bucketed"] = timed(prior_draws, reps=1)
+    out["posterior_spread_0.2_W262144_bucketed"] = timed(np.clip(truth + 0.2 * rng.randn(1 << 18, 6), PRIOR_LOWER, PRIOR_UPPER))
+    lk.set_bucketing(False)
+    out["posterior_spread_0.2_W262144"] = timed(np.clip(truth + 0.2 * rng.randn(1 << 18, 6), PRIOR_LOWER, PRIOR_UPPER))
 
     # ---- configs[2] shape: 15 independent short-GRB fits (packaged model, "S" grid, the sample's points per
     # burst), bursts dealt round-robin to the ranks, no communication.  Synthetic light curves on log-uniform

@@ -9,6 +9,7 @@
 //   rhs_kernel                    the coupled reference RHS for ODEs()/odes() callers
 //   dfma_peak_kernel              FP64 FMA roofline denominator
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <cstdio>
 #include <cstring>
@@ -42,6 +43,7 @@ struct KernelArgs {
   int* n_rhs;           // [W] or null
   double* out;          // mode-dependent
   double* state;        // curves: [W][2][Gs] or null
+  const int* order;     // [W] or null: thread i evaluates walker order[i] (walkers bucketed by a cost key)
   int* queue;           // [W] walkers deferred to the stiff launch
   int* queue_count;     // [1]
 };
@@ -51,7 +53,14 @@ struct KernelArgs {
 // gathers).
 template <int BLOCK>
 __device__ __forceinline__ void stage_theta(const double* __restrict__ theta, int W, int ndim,
-                                            double* s_theta) {
+                                            double* s_theta, const int* __restrict__ order) {
+  if (order) {      // bucketed launch: each thread gathers its own row
+    const int i = blockIdx.x * BLOCK + threadIdx.x;
+    const long long w = (i < W) ? order[i] : 0;
+    for (int d = 0; d < ndim; ++d) s_theta[threadIdx.x * ndim + d] = (i < W) ? theta[w * ndim + d] : 0.0;
+    __syncthreads();
+    return;
+  }
   const long long base = (long long)blockIdx.x * BLOCK * ndim;
   const long long total = (long long)W * ndim;
   for (int i = threadIdx.x; i < BLOCK * ndim; i += BLOCK) {
@@ -119,10 +128,11 @@ eval_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ double s_buf[NodeBuf<MODE>::n * BLOCK];
   __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
   __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];   // per-warp broadcast slot (curve output)
-  stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta);
-  const int w = blockIdx.x * BLOCK + threadIdx.x;
+  stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta, a.order);
+  const int slot = blockIdx.x * BLOCK + threadIdx.x;
+  const int w = (a.order && slot < a.W) ? a.order[slot] : slot;
   void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
-  if (eval_one<MODE, BLOCK, false>(a, w < a.W, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch))
+  if (eval_one<MODE, BLOCK, false>(a, slot < a.W, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch))
     a.queue[atomicAdd(a.queue_count, 1)] = w;
 }
 
@@ -372,7 +382,13 @@ struct mp_handle {
     int* queue = nullptr;        // walkers deferred to the stiff launch
     int* queue_count = nullptr;
     size_t cap_queue = 0;
+    // walker bucketing (mp_set_bucketing): sort keys / walker ids (double-buffered) and CUB's scratch
+    unsigned *key_in = nullptr, *key_out = nullptr;
+    int *id_in = nullptr, *id_out = nullptr;
+    void* sort_tmp = nullptr;
+    size_t cap_sort = 0, cap_tmp = 0;
   } lanes[2];
+  int bucketing = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;   // == lanes[0].stream
 };
@@ -469,6 +485,7 @@ extern "C" void mp_destroy(mp_handle* h) {
   cudaFree(h->s_status); cudaFree(h->s_nrhs);
   for (auto& L : h->lanes) {
     cudaFree(L.queue); cudaFree(L.queue_count);
+    cudaFree(L.key_in); cudaFree(L.key_out); cudaFree(L.id_in); cudaFree(L.id_out); cudaFree(L.sort_tmp);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
   delete h;
@@ -477,6 +494,12 @@ extern "C" void mp_destroy(mp_handle* h) {
 extern "C" int mp_set_prior(mp_handle* h, const mp_prior_spec* prior) {
   if (!h || !prior) return fail(MP_ERR_BAD_ARG, "mp_set_prior: null pointer");
   h->prior = *prior;
+  return MP_OK;
+}
+
+extern "C" int mp_set_bucketing(mp_handle* h, int32_t enabled) {
+  if (!h) return fail(MP_ERR_BAD_ARG, "mp_set_bucketing: null handle");
+  h->bucketing = enabled ? 1 : 0;
   return MP_OK;
 }
 
@@ -523,6 +546,55 @@ static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream
 // grid of the stiff-bucket launch: one block per batch of the longest possible queue
 static int stiff_grid(const mp_handle*, int W, int block) { return (W + block - 1) / block; }
 
+// ---- walker bucketing ------------------------------------------------------------------------
+// The step count of a walker grows with the mass that flows through the disc (log MdiscI + log delta:
+// correlation 0.58 / 0.52 with log-steps over the prior box) and, second, with the disc
+// radius (the viscous time).  In an ensemble that is spread out the lanes of a warp therefore finish at
+// very different times (prior-uniform: the slowest lane of a warp does 3.2x the mean).  With bucketing on,
+// the walkers of a launch are ordered by that key (quarter-decade bins of the mass flow, then radius) and
+// thread i evaluates walker order[i]: similar walkers share a warp.  Measured on B200: prior-uniform
+// ensembles +35 %, posterior-like spreads +5..20 %, a 1e-4 ball -2 % (the sort) -- hence opt-in.
+__global__ void bucket_key_kernel(const double* __restrict__ theta, int W, int ndim, int unlog_mask,
+                                  unsigned* __restrict__ key, int* __restrict__ id) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= W) return;
+  const double* th = theta + (size_t)i * ndim;
+  const double lm = ((unlog_mask >> 2) & 1) ? th[2] : log10(th[2]);
+  const double lr = ((unlog_mask >> 3) & 1) ? th[3] : log10(th[3]);
+  const double ld = ((unlog_mask >> 5) & 1) ? th[5] : log10(th[5]);
+  const double flow = fmin(fmax((lm + ld + 16.0) * 4.0, 0.0), 255.0);     // quarter-decade bins
+  const double rad = fmin(fmax(lr * 8192.0, 0.0), 65535.0);
+  const unsigned k = ((unsigned)(flow == flow ? flow : 0.0) << 16) | (unsigned)(rad == rad ? rad : 0.0);
+  key[i] = k;
+  id[i] = i;
+}
+
+static int bucket_walkers(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane) {
+  mp_handle::Lane& L = h->lanes[lane];
+  const size_t W = (size_t)a.W;
+  if (W > L.cap_sort) {
+    cudaFree(L.key_in); cudaFree(L.key_out); cudaFree(L.id_in); cudaFree(L.id_out);
+    L.key_in = L.key_out = nullptr; L.id_in = L.id_out = nullptr; L.cap_sort = 0;
+    MP_CUDA(cudaMalloc((void**)&L.key_in, W * sizeof(unsigned)));
+    MP_CUDA(cudaMalloc((void**)&L.key_out, W * sizeof(unsigned)));
+    MP_CUDA(cudaMalloc((void**)&L.id_in, W * sizeof(int)));
+    MP_CUDA(cudaMalloc((void**)&L.id_out, W * sizeof(int)));
+    L.cap_sort = W;
+  }
+  size_t need = 0;
+  MP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, L.key_in, L.key_out, L.id_in, L.id_out, (int)W, 0, 24, stream));
+  if (need > L.cap_tmp) {
+    cudaFree(L.sort_tmp);
+    L.sort_tmp = nullptr; L.cap_tmp = 0;
+    MP_CUDA(cudaMalloc(&L.sort_tmp, need));
+    L.cap_tmp = need;
+  }
+  bucket_key_kernel<<<(a.W + 255) / 256, 256, 0, stream>>>(a.theta, a.W, a.ndim, a.sp.unlog_mask, L.key_in, L.id_in);
+  MP_CUDA(cub::DeviceRadixSort::SortPairs(L.sort_tmp, need, L.key_in, L.key_out, L.id_in, L.id_out, (int)W, 0, 24, stream));
+  a.order = L.id_out;
+  return MP_OK;
+}
+
 // Every walker onto the stiff queue: a spec the explicit kernel does not implement (Bucciantini torque).
 __global__ void queue_all_kernel(int* queue, int* count, int W, const int* ids = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -541,6 +613,7 @@ static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lan
     MP_CUDA(cudaGetLastError());
     return MP_OK;
   }
+  if (h->bucketing && MODE != kModeCurves && a.W >= 2048 && (rc = bucket_walkers(h, a, stream, lane))) return rc;
   // small ensembles: 32-thread blocks spread the warps over more SMs
   if (a.W <= 148 * 64 * 4) {
     eval_kernel<MODE, 32><<<(a.W + 31) / 32, 32, 0, stream>>>(a);

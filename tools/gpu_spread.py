@@ -9,13 +9,20 @@ from oracle import magprop_oracle as O
 g = np.load(os.path.join(ROOT, "tests/golden/lnprob_script.npz"))
 name = os.environ.get("DS", "Classic"); W = int(os.environ.get("W", 1 << 18))
 lk = Likelihood(A.script_model_spec(), time_grid(None), g[f"{name}_x"], g[f"{name}_y"], g[f"{name}_yerr"], O.SCRIPT_LOWER, O.SCRIPT_UPPER)
+if os.environ.get("BUCKET"): lk.set_bucketing(True)
 rng = np.random.RandomState(5)
 truth = O.SYNTH_TRUTHS_LOG[name]
 cases = {"ball 1e-4": truth + 1e-4 * rng.randn(W, 6),
          "spread 0.01": np.clip(truth + 0.01 * rng.randn(W, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER),
          "spread 0.05": np.clip(truth + 0.05 * rng.randn(W, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER),
          "spread 0.2": np.clip(truth + 0.2 * rng.randn(W, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER)}
+if os.environ.get("PRIOR"):
+    cases["prior uniform"] = rng.uniform(O.SCRIPT_LOWER, O.SCRIPT_UPPER, size=(W, 6))
+key = os.environ.get("SORT")
 for label, th in cases.items():
+    if key == "md": th = th[np.argsort(th[:, 2] + th[:, 5])]
+    if key == "r": th = th[np.argsort(th[:, 3])]
+    if key == "mdr": th = th[np.lexsort((th[:, 3], np.round((th[:, 2] + th[:, 5]) * 4)))]
     d_th = torch.from_numpy(np.ascontiguousarray(th)).cuda(); d_l = torch.empty(W, dtype=torch.float64, device="cuda"); d_n = torch.empty(W, dtype=torch.int32, device="cuda")
     for _ in range(2): lk.lnprob_device(d_th.data_ptr(), W, 6, d_l.data_ptr(), 0, d_n.data_ptr())
     torch.cuda.synchronize()
