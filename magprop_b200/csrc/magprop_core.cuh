@@ -763,6 +763,12 @@ MP_HD double dense_eval(const Integrator& in, double tq) {
   const double th1 = 1.0 - th;
   return fma(th, fma(th1, fma(th, fma(th1, in.r5, in.r4), in.r3), in.r2), in.r1);
 }
+// The same with 1/hs supplied: a run of nodes inside one step shares the division.
+MP_HD double dense_eval_r(const Integrator& in, double tq, double ihs) {
+  const double th = (tq - in.t0) * ihs;
+  const double th1 = 1.0 - th;
+  return fma(th, fma(th1, fma(th, fma(th1, in.r5, in.r4), in.r3), in.r2), in.r1);
+}
 
 // f(t, omega) out of line: used by the (cold) initialisation only, so the hot
 // step loop below holds the single inlined copy of disc_at + spin_rhs.
@@ -1441,11 +1447,14 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
     for (;;) {
       bool step = false;
       if (integrate && !deferred && jn < c1) {
-        while (jn < c1) {
-          const double tn = ldg(dv.node_t + jn);
-          if (!(tn <= in.t)) break;
-          buf[(jn - c0) * bstride] = dense_eval(in, tn);
-          ++jn;
+        double tn = ldg(dv.node_t + jn);
+        if (tn <= in.t) {
+          const double ihs = 1.0 / in.hs;
+          do {
+            buf[(jn - c0) * bstride] = dense_eval_r(in, tn, ihs);
+            if (++jn >= c1) break;
+            tn = ldg(dv.node_t + jn);
+          } while (tn <= in.t);
         }
         if (jn < c1) {
           if (in.status != kWalkerOk) {
@@ -1484,13 +1493,13 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
         if (j < c1) {
           const double tn = ldg(dv.node_t + j);
           const double v = buf[lane * bstride + (src - lane)];         // column of lane `src`, row `lane`
-          const double om = sw->bad ? ((tn == dv.t_start) ? sw->omega0 : NAN) : (STIFF ? v : 1.0 / sqrt(v));
+          const double om = sw->bad ? ((tn == dv.t_start) ? sw->omega0 : NAN) : (STIFF ? v : rsqrt_pos(v));
           const double M = sw->bad ? ((tn == dv.t_start) ? sw->M_init : NAN)
                                    : ((sp.lum_dipole_only && !so) ? 0.0 : disc_mass(*sw, tn));
           const Lum L = luminosity(sp, *sw, M, om);
-          o[j] = L.tot / 1.0e50;
-          o[Nn + j] = L.prop / 1.0e50;
-          o[2 * Nn + j] = L.dip / 1.0e50;
+          o[j] = L.tot * 1.0e-50;            // (/1e50, funcs.py:231,236, as one multiplication: <= 1 ulp)
+          o[Nn + j] = L.prop * 1.0e-50;
+          o[2 * Nn + j] = L.dip * 1.0e-50;
           if (so) {
             so[j] = M;
             so[Nn + j] = om;
@@ -1516,9 +1525,9 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
       }
       const Lum L = luminosity(sp, w, M, om);
       if (MODE == kModeCurves) {
-        out[(0 * Nn + j) * ostride] = L.tot / 1.0e50;
-        out[(1 * Nn + j) * ostride] = L.prop / 1.0e50;
-        out[(2 * Nn + j) * ostride] = L.dip / 1.0e50;
+        out[(0 * Nn + j) * ostride] = L.tot * 1.0e-50;
+        out[(1 * Nn + j) * ostride] = L.prop * 1.0e-50;
+        out[(2 * Nn + j) * ostride] = L.dip * 1.0e-50;
         if (state_out) {
           state_out[(0 * Nn + j) * ostride] = M;
           state_out[(1 * Nn + j) * ostride] = om;
@@ -1539,7 +1548,7 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
             const double r = fma(-mod, ldg(dv.dat_c + idat), ldg(dv.dat_ys + idat));   // (y - mod/1e50)/yerr
             chi2 = fma(r, r, chi2);
           } else {
-            out[(dat_orig ? dat_orig[idat] : idat) * ostride] = mod / 1.0e50;
+            out[(dat_orig ? dat_orig[idat] : idat) * ostride] = mod * 1.0e-50;
           }
           ++idat;
         }

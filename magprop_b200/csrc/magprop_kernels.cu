@@ -44,6 +44,7 @@ struct KernelArgs {
   double* out;          // mode-dependent
   double* state;        // curves: [W][2][Gs] or null
   const int* order;     // [W] or null: thread i evaluates walker order[i] (walkers bucketed by a cost key)
+  int lanes_per_walker; // curve output: one walker per this many lanes (1, 2, .. 32), see launch_eval
   int* queue;           // [W] walkers deferred to the stiff launch
   int* queue_count;     // [1]
 };
@@ -53,11 +54,13 @@ struct KernelArgs {
 // gathers).
 template <int BLOCK>
 __device__ __forceinline__ void stage_theta(const double* __restrict__ theta, int W, int ndim,
-                                            double* s_theta, const int* __restrict__ order) {
-  if (order) {      // bucketed launch: each thread gathers its own row
-    const int i = blockIdx.x * BLOCK + threadIdx.x;
-    const long long w = (i < W) ? order[i] : 0;
-    for (int d = 0; d < ndim; ++d) s_theta[threadIdx.x * ndim + d] = (i < W) ? theta[w * ndim + d] : 0.0;
+                                            double* s_theta, const int* __restrict__ order, int lpw) {
+  if (order || lpw > 1) {      // bucketed launch / sparse warps: each thread gathers its own row
+    const int slot = blockIdx.x * BLOCK + threadIdx.x;
+    const int i = slot / lpw;
+    const bool have = (i < W) && (slot % lpw == 0);
+    const long long w = have ? (order ? order[i] : i) : 0;
+    for (int d = 0; d < ndim; ++d) s_theta[threadIdx.x * ndim + d] = have ? theta[w * ndim + d] : 0.0;
     __syncthreads();
     return;
   }
@@ -128,11 +131,14 @@ eval_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ double s_buf[NodeBuf<MODE>::n * BLOCK];
   __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
   __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];   // per-warp broadcast slot (curve output)
-  stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta, a.order);
+  const int lpw = (MODE == kModeCurves && a.lanes_per_walker > 1) ? a.lanes_per_walker : 1;
+  stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta, a.order, lpw);
   const int slot = blockIdx.x * BLOCK + threadIdx.x;
-  const int w = (a.order && slot < a.W) ? a.order[slot] : slot;
+  const int i = slot / lpw;
+  const bool have = (i < a.W) && (slot % lpw == 0);
+  const int w = (a.order && have) ? a.order[i] : i;
   void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
-  if (eval_one<MODE, BLOCK, false>(a, slot < a.W, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch))
+  if (eval_one<MODE, BLOCK, false>(a, have, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch))
     a.queue[atomicAdd(a.queue_count, 1)] = w;
 }
 
@@ -614,6 +620,21 @@ static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lan
     return MP_OK;
   }
   if (h->bucketing && MODE != kModeCurves && a.W >= 2048 && (rc = bucket_walkers(h, a, stream, lane))) return rc;
+  if (MODE == kModeCurves) {
+    // Curve output is dominated by the luminosity stage at up to 10 001 nodes, which a warp works through
+    // one walker at a time with one node per lane.  With few walkers (a full-grid launch is bounded by its
+    // 240 KB of output per walker) 32 walkers per warp leave most schedulers empty, so the walkers are
+    // spread one per 2..32 lanes until the launch holds ~16 warps per SM (measured: 16 384 full-grid curves,
+    // 3.5 warps per SM and 9 % FP64 pipe with dense warps).
+    int lpw = 1;
+    while (lpw < 32 && (long long)a.W * lpw * 2 <= (long long)h->sm_count * 16 * 32) lpw *= 2;
+    a.lanes_per_walker = lpw;
+    const long long threads = (long long)a.W * lpw;
+    eval_kernel<MODE, 32><<<(unsigned)((threads + 31) / 32), 32, 0, stream>>>(a);
+    eval_stiff_kernel<MODE, 32><<<stiff_grid(h, a.W, 32), 32, 0, stream>>>(a);
+    MP_CUDA(cudaGetLastError());
+    return MP_OK;
+  }
   // small ensembles: 32-thread blocks spread the warps over more SMs
   if (a.W <= 148 * 64 * 4) {
     eval_kernel<MODE, 32><<<(a.W + 31) / 32, 32, 0, stream>>>(a);
