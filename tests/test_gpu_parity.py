@@ -263,6 +263,21 @@ def test_ten_million_walkers_config5_size(built, golden):
     lk.close()
 
 
+def test_curves_independent_of_launch_shape(built):
+    """Curve launches spread their walkers one per 1..32 lanes depending on the launch size; a walker's curve must
+    not depend on that (same bits from a 1-, 5-, 33-, 700- and 5000-walker launch, with and without state output)."""
+    rng = np.random.RandomState(17)
+    lk = Likelihood(A.script_model_spec(unlog=False), time_grid(None))
+    pars = np.column_stack([rng.uniform(0.5, 5, 5000), rng.uniform(1, 8, 5000), 10 ** rng.uniform(-4, -2.5, 5000),
+                            10 ** rng.uniform(2, 3, 5000), 10 ** rng.uniform(-1, 1, 5000), 10 ** rng.uniform(-0.5, 1.5, 5000)])
+    big, st_big = lk.curves(pars, node_stride=100)
+    for n in (1, 5, 33, 700):
+        out, state, st = lk.curves(pars[:n], node_stride=100, with_state=True)
+        assert np.array_equal(out, big[:n], equal_nan=True) and (st == st_big[:n]).all()
+        assert state.shape == (n, 2, out.shape[2]) and np.isfinite(state[st == 0]).all()
+    lk.close()
+
+
 def test_bucketing_is_transparent(built, golden):
     """mp_set_bucketing orders the walkers of a launch by a cost key; every walker's result must be bit-identical
     to the unbucketed launch and come back in the caller's order (prior-uniform ensemble incl. prior rejects,
