@@ -120,6 +120,13 @@ int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int32_t ndim,
 /* Device-pointer form: all pointers are device addresses on the handle's device
  * (e.g. torch.Tensor.data_ptr()); enqueues on `stream` (a cudaStream_t, NULL =
  * default stream) and returns without synchronising.                           */
+/* The same without the final wait: the copies and launches are queued on the handle's two streams and the
+ * call returns; the outputs are valid after mp_synchronize(h).  Lets one host thread keep several handles
+ * (independent datasets / bursts, BASELINE configs[2]) in flight at once; the caller's buffers must stay alive
+ * and, for the copies to overlap, be pinned.  mp_lnprob_batch == mp_lnprob_batch_async + mp_synchronize.   */
+int mp_lnprob_batch_async(mp_handle* h, const double* theta, int32_t W, int32_t ndim,
+                          double* lnp, int32_t* status, int32_t* n_rhs);
+int mp_synchronize(mp_handle* h);
 int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32_t W, int32_t ndim,
                            double* d_lnp, int32_t* d_status, int32_t* d_n_rhs,
                            void* stream);

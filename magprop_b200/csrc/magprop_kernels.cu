@@ -664,8 +664,8 @@ extern "C" int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32
 // One full wave of the explicit kernel: 8 resident 64-thread blocks per SM.
 static int wave_walkers(const mp_handle* h) { return h->sm_count * MP_MIN_BLOCKS_64 * 64; }
 
-extern "C" int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int32_t ndim, double* lnp,
-                               int32_t* status, int32_t* n_rhs) {
+extern "C" int mp_lnprob_batch_async(mp_handle* h, const double* theta, int32_t W, int32_t ndim, double* lnp,
+                                     int32_t* status, int32_t* n_rhs) {
   if (!h || (W > 0 && (!theta || !lnp))) return fail(MP_ERR_BAD_ARG, "mp_lnprob_batch: null pointer");
   if (ndim < 6 || ndim > MP_MAX_NDIM) return fail(MP_ERR_BAD_ARG, "ndim must be 6, 7, 8 or 9");
   if (W == 0) return MP_OK;
@@ -706,9 +706,22 @@ extern "C" int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int
     if (n_rhs) MP_CUDA(cudaMemcpyAsync(n_rhs + c0, h->s_nrhs + c0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (n != chunk) break;
   }
+  return MP_OK;
+}
+
+extern "C" int mp_synchronize(mp_handle* h) {
+  if (!h) return fail(MP_ERR_BAD_ARG, "mp_synchronize: null handle");
+  MP_CUDA(cudaSetDevice(h->device));
   MP_CUDA(cudaStreamSynchronize(h->lanes[0].stream));
   MP_CUDA(cudaStreamSynchronize(h->lanes[1].stream));
   return MP_OK;
+}
+
+extern "C" int mp_lnprob_batch(mp_handle* h, const double* theta, int32_t W, int32_t ndim, double* lnp,
+                               int32_t* status, int32_t* n_rhs) {
+  const int rc = mp_lnprob_batch_async(h, theta, W, ndim, lnp, status, n_rhs);
+  if (rc) return rc;
+  return (W > 0) ? mp_synchronize(h) : MP_OK;
 }
 
 extern "C" int mp_model_at_data(mp_handle* h, const double* pars, int32_t W, int32_t ndim, double* out,

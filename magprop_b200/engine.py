@@ -95,6 +95,17 @@ class Likelihood:
             return lnp, status, nrhs
         return float(lnp[0]) if single else lnp
 
+    def lnprob_async(self, theta: np.ndarray, lnp: np.ndarray, status=None, nrhs=None):
+        """Queue lnprob of theta[W, ndim] into the caller's (ideally pinned) float64 buffer ``lnp`` and return
+        at once; the result is valid after ``synchronize()``.  Several handles can be in flight together."""
+        W, ndim = theta.shape
+        A.check(self._lib.mp_lnprob_batch_async(self._h, A.ptr(theta), W, ndim, A.ptr(lnp),
+                                                A.ptr(status) if status is not None else None,
+                                                A.ptr(nrhs) if nrhs is not None else None))
+
+    def synchronize(self):
+        A.check(self._lib.mp_synchronize(self._h))
+
     def lnprob_device(self, d_theta: int, W: int, ndim: int, d_lnp: int, d_status: int = 0, d_nrhs: int = 0,
                       stream: int = 0):
         """Enqueue lnprob on device buffers (raw pointers); does not synchronise."""

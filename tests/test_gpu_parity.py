@@ -278,6 +278,26 @@ def test_curves_independent_of_launch_shape(built):
     lk.close()
 
 
+def test_async_host_pointer_calls_overlap_handles(built, golden):
+    """mp_lnprob_batch_async + mp_synchronize: three datasets' handles queued from one thread give the same bits
+    as the synchronous call."""
+    g = golden["lnprob_script"]
+    rng = np.random.RandomState(31)
+    W = 200000                                     # > one wave: exercises the two-lane chunking
+    liks, thetas, outs, want = {}, {}, {}, {}
+    for name in ("Classic", "Sloped", "Stuttering"):
+        liks[name] = script_lik(g, name)
+        thetas[name] = np.ascontiguousarray(O.SYNTH_TRUTHS_LOG[name] + 1e-3 * rng.randn(W, 6))
+        want[name] = liks[name].lnprob(thetas[name])
+        outs[name] = np.full(W, np.nan)
+    for name in liks:
+        liks[name].lnprob_async(thetas[name], outs[name])
+    for name in liks:
+        liks[name].synchronize()
+        assert np.array_equal(outs[name], want[name])
+        liks[name].close()
+
+
 def test_bucketing_is_transparent(built, golden):
     """mp_set_bucketing orders the walkers of a launch by a cost key; every walker's result must be bit-identical
     to the unbucketed launch and come back in the caller's order (prior-uniform ensemble incl. prior rejects,
