@@ -76,6 +76,8 @@ struct Spec {
   // explicit step, which integrates y = omega^-2 (see spin_g): doubled lever arms, 2n, and the
   // break-up boundary in y
   double sqrtGM2, sqrt_GMR2, sGMkc2, rhs_n2, y_breakup_rhs;
+  // spin_g's scaling (see there): qa and ni factors, k c and R over GM^(1/3), lever-arm constants
+  double g_qa, g_ni, g_kc, g_R, g_floor, g_cap;
   int lprop_binding_term;
   int bucciantini;             // RHS dipole torque of Bucciantini et al. 2006 (figure_3.py:142-143): classical x 4 (Rlc/Rm)^3
   double bucc_cap;             // 4/k^3: that factor where Rm is capped at k*Rlc
@@ -249,6 +251,7 @@ struct Walker {
   double sqrtA;    // sqrt(A_rm)
   double KqA;      // Kq * sqrtA : late-phase qa = KqA * Q(u)
   double tvI;      // 1/(tvisc I) : ni = Mdisc * tvI
+  double g_sqrtA, g_tvI;   // sqrtA and tvI in spin_g's scaling (explicit variant)
   double KtvI;     // K/(tvisc I) : late-phase ni = KtvI * S(u)
   // luminosity stage (its own alpha/cs7/k/n may differ from the RHS's)
   double l_inv_tv, l_A_rm, l_Cw, l_Ccap, l_kc;
@@ -430,6 +433,8 @@ MP_HD void walker_setup(const Spec& sp, const double* pars, double dipeff, doubl
   w.KqA = w.Kq * w.sqrtA;
   w.tvI = w.inv_tv * sp.inv_inertia;
   w.KtvI = w.K * w.tvI;
+  w.g_sqrtA = w.sqrtA * sp.g_qa;
+  w.g_tvI = w.tvI * sp.g_ni;
   w.sGMkc = sqrt(kGM * w.kc);
   w.Ldip_coef = (mu * mu) / (6.0 * (kC * kC * kC));
   w.Cdip_I = w.Ldip_coef * sp.inv_inertia;
@@ -646,6 +651,37 @@ MP_HD double exp_small(double x) {
   return bitsd(dbits(p) + ((int64_t)k << 52));
 }
 
+// exp(x) for |x| <= 40 to ~2e-13 relative (degree 10): the spin chain's tanh needs no more.
+MP_HD double exp_small10(double x) {
+  const double kd = fma(x, kExpR[0], kExpR[1]);
+  const int k = (int)(dbits(kd) & 0xffffffffLL);
+  const double kf = kd - kExpR[1];
+  double r = fma(kf, kExpR[2], x);
+  r = fma(kf, kExpR[3], r);
+  const double r2 = r * r;
+  double ev = kExpC[10], od = kExpC[9];
+  ev = fma(ev, r2, kExpC[8]);
+  od = fma(od, r2, kExpC[7]);
+  ev = fma(ev, r2, kExpC[6]);
+  od = fma(od, r2, kExpC[5]);
+  ev = fma(ev, r2, kExpC[4]);
+  od = fma(od, r2, kExpC[3]);
+  ev = fma(ev, r2, kExpC[2]);
+  od = fma(od, r2, kExpC[1]);
+  ev = fma(ev, r2, kExpC[0]);
+  const double p = fma(od, r, ev);
+  return bitsd(dbits(p) + ((int64_t)k << 52));
+}
+MP_HD double rcp_pos2(double x) {       // 1/x for 1 <= x, ~2^-44 (one Newton step on the MUFU seed)
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return fma(r, fma(-x, r, 1.0), r);
+#else
+  return 1.0 / x;
+#endif
+}
+
 // Disc quantities of one Runge-Kutta stage, in the folded form spin_f wants.
 struct StageDisc {
   double qa;   // sqrt(A_rm) * Mdisc^(-1/7)
@@ -700,33 +736,44 @@ MP_HD double spin_f(const Spec& sp, const Walker& w, const StageDisc& d, double 
 // whose right-hand side carries the option -- the kernels route every walker there, so this hot function
 // pays nothing for a figure-script variant.)
 MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double y, unsigned& side, unsigned& regime) {
+  // d is in the explicit variant's scaling (disc_stages_dp5 / scale_for_g):
+  //   d.qa = GM^(-1/6) sqrt(A_rm) Mdisc^(-1/7)   so that  Rm = GM^(1/3) qa^2,  w = qa^3 omega (uncapped)
+  //   d.ni = 2 GM^(2/3) Mdisc/(tvisc I)          so that  2 sqrt(GM Rm) Mdisc/(tvisc I) = qa d.ni
+  // which removes three multiplications by constants from every evaluation.
   const double om = rsqrt_pos(y);                              // omega
   const double iom = y * om;                                   // 1/omega
-  const double rm = d.qa * d.qa;                               // uncapped Alfven radius
-  const double rcap = sp.kc * iom;                             // k*Rlc
-  double fast, lever2;                                         // fastness w, 2 sqrt(GM Rm)
+  const double rm = d.qa * d.qa;                               // uncapped Alfven radius / GM^(1/3)
+  const double rcap = sp.g_kc * iom;                           // k*Rlc / GM^(1/3)
+  double fast, lev;                                            // fastness w; 2 sqrt(GM Rm) Mdisc/(tvisc I) = lev * d.ni
   if (rm >= rcap) {                                            // Rm >= k*Rlc (funcs.py:109-110)
     const double r = rsqrt_pos(om);
     fast = sp.Ccap * r;
-    const bool floor_ = !(rcap >= kR);
-    lever2 = floor_ ? sp.sqrt_GMR2 : sp.sGMkc2 * r;
+    const bool floor_ = !(rcap >= sp.g_R);
+    lev = floor_ ? sp.g_floor : sp.g_cap * r;
     regime = floor_ ? 3u : 1u;
   } else {                                                     // (also taken by a NaN qa, which then reaches the result)
-    fast = (rm * d.qa) * (sp.inv_sqrtGM * om);
-    const bool floor_ = rm < kR;
-    lever2 = floor_ ? sp.sqrt_GMR2 : sp.sqrtGM2 * d.qa;        // funcs.py:135-138
+    fast = (rm * d.qa) * om;
+    const bool floor_ = rm < sp.g_R;
+    lev = floor_ ? sp.g_floor : d.qa;                          // funcs.py:135-138
     regime = floor_ ? 2u : 0u;
   }
-  // tanh(n (w - 1)) to 4e-16 absolute; beyond |2x| = 38.2 it is +-1 to the last bit
+  // tanh(n (w - 1)); beyond |2x| = 38.2 it is +-1 to the last bit.  Inside, 1e-13 absolute is ample for the
+  // integrator (the luminosity stage has its own, full-precision evaluation): degree-10 exp, second-order
+  // reciprocal.
   const double x2 = fma(sp.rhs_n2, fast, -sp.rhs_n2);
   double th;
-  if (x2 > 38.2) th = 1.0;
-  else if (x2 < -38.2) th = -1.0;
-  else th = fma(-2.0, rcp_pos(exp_small(x2) + 1.0), 1.0);
+  if (fabs(x2) > 38.2) th = copysign(1.0, x2);
+  else th = fma(-2.0, rcp_pos2(exp_small10(x2) + 1.0), 1.0);
   const bool above = y < sp.y_breakup_rhs;                     // rot_param > 0.27 (funcs.py:131-132)
   side |= above ? 2u : 1u;
   th = above ? 0.0 : th;
-  return fma((lever2 * d.ni) * (y * iom), th, w.Cdip_I2);
+  return fma((lev * d.ni) * (y * iom), th, w.Cdip_I2);
+}
+
+// Generic disc quantities (disc_stages<N>) -> the scaling spin_g wants.
+MP_HD void scale_for_g(const Spec& sp, StageDisc& d) {
+  d.qa *= sp.g_qa;
+  d.ni *= sp.g_ni;
 }
 
 MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double y, unsigned& side) {
@@ -789,6 +836,7 @@ __device__ __host__ __noinline__
 static double spin_g_cold(const Spec& sp, const Walker& w, double t, double y, unsigned* regime) {
   StageDisc d;
   disc_stages<1>(w, &t, &d);
+  scale_for_g(sp, d);
   unsigned side = 0u, rg = 0u;
   const double g = spin_g(sp, w, d, y, side, rg);
   if (regime) *regime = rg;
@@ -934,22 +982,22 @@ static double locate_kink(const Spec& sp, const Walker& w, double t, double h, d
   const bool cap_event = ((r0 ^ r1) & 1u) != 0u;
   const bool capped = (r0 & 1u) != 0u;            // used by the floor event only (cap bit equal at both ends)
   // margin(theta): changes sign where the bit flips
-  auto margin = [&](double th, double qa) {
+  auto margin = [&](double th, double qa) {          // qa in spin_g's scaling
     const double yy = fma(th, ynew - y, y);
     const double rm = qa * qa;
-    const double rcap = sp.kc * (yy * rsqrt_pos(yy));
-    return cap_event ? rm - rcap : (capped ? kR - rcap : kR - rm);
+    const double rcap = sp.g_kc * (yy * rsqrt_pos(yy));
+    return cap_event ? rm - rcap : (capped ? sp.g_R - rcap : sp.g_R - rm);
   };
   StageDisc d;
   disc_stages<1>(w, &t, &d);
-  double a = 0.0, b = 1.0, fa = margin(0.0, d.qa), fb = margin(1.0, qa_end);
+  double a = 0.0, b = 1.0, fa = margin(0.0, d.qa * sp.g_qa), fb = margin(1.0, qa_end);
   if (!(fa * fb < 0.0)) return -1.0;              // also NaN
 #pragma unroll
   for (int it = 0; it < 2; ++it) {
     const double th = (a * fb - b * fa) / (fb - fa);
     const double tt = fma(th, h, t);
     disc_stages<1>(w, &tt, &d);
-    const double m = margin(th, d.qa);
+    const double m = margin(th, d.qa * sp.g_qa);
     if (!(m == m)) return -1.0;
     if ((m < 0.0) == (fa < 0.0)) { a = th; fa = m; }
     else { b = th; fb = m; }
@@ -1104,7 +1152,7 @@ MP_HD void disc_stages(const Walker& w, const double* ts, StageDisc* d) {
 // the transient has died out (u >= u_late) the table's Q = S^(-1/7) would serve as well as the seeded
 // x^(-1/7) at the same cost; keeping a single form means the lanes of a warp never split over the phase
 // (measured: +11 % on ensembles spread around the posterior, +5 % on a 1e-4 ball).
-MP_HD void disc_stages_dp5(const Walker& w, const double* ts, double Et, double dl, StageDisc* d, double& Eend) {
+MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, double Et, double dl, StageDisc* d, double& Eend) {
   double u[5];
   TableAt ta[5];
   bool in_all = true;
@@ -1115,6 +1163,8 @@ MP_HD void disc_stages_dp5(const Walker& w, const double* ts, double Et, double 
   }
   if (!in_all) {                                        // parameters far outside the prior box
     disc_stages<5>(w, ts, d);
+#pragma unroll
+    for (int s = 0; s < 5; ++s) scale_for_g(sp, d[s]);
     Eend = exp_c(w.u0 - u[4]);
     return;
   }
@@ -1126,8 +1176,8 @@ MP_HD void disc_stages_dp5(const Walker& w, const double* ts, double Et, double 
   for (int s = 0; s < 5; ++s) {
     const double S = poly10p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
     const double M = fma(w.K, S, w.C * E[s]);
-    d[s].ni = M * w.tvI;
-    d[s].qa = w.sqrtA * pow_m17_seeded(M);
+    d[s].ni = M * w.g_tvI;
+    d[s].qa = w.g_sqrtA * pow_m17_seeded(M);
   }
   Eend = E[4];
 }
@@ -1145,7 +1195,7 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   const double ts[5] = {fma(DP::c2(), h, t), fma(DP::c3(), h, t), fma(DP::c4(), h, t), fma(DP::c5(), h, t), tn};
   StageDisc d[5];
   double Eend;
-  disc_stages_dp5(w, ts, in.E, (tn - t) * w.inv_tv, d, Eend);
+  disc_stages_dp5(sp, w, ts, in.E, (tn - t) * w.inv_tv, d, Eend);
   // (One shared copy of the chain: inlining it after each disc block lets the compiler overlap the
   // two, but lanes of a warp that sit in different phases then run the chain twice -- measured
   // 4 % slower on uniform ensembles, 11 % on spread ones.)

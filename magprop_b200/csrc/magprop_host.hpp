@@ -43,6 +43,15 @@ inline Spec make_spec(const mp_model_spec& m) {
   s.sGMkc2 = 2.0 * s.sGMkc;
   s.rhs_n2 = 2.0 * s.rhs_n;
   s.y_breakup_rhs = 1.0 / s.omega2_breakup_rhs;
+  {                                                           // spin_g's scaling
+    const double gm13 = std::cbrt(kGM), gm16 = std::sqrt(gm13);
+    s.g_qa = 1.0 / gm16;
+    s.g_ni = 2.0 * gm13 * gm13;                              // 2 GM^(2/3) = 2 sqrt(GM) GM^(1/6)
+    s.g_kc = s.kc / gm13;
+    s.g_R = kR / gm13;
+    s.g_floor = s.sqrt_GMR2 / s.g_ni;                        // lever arm at its floor: 2 sqrt(GM R) / (2 GM^(2/3))
+    s.g_cap = s.sGMkc2 / s.g_ni;                             // capped lever arm: 2 sqrt(GM k c) r / (2 GM^(2/3))
+  }
   s.bucciantini = m.dipole_torque ? 1 : 0;
   s.bucc_cap = 4.0 / (m.rhs_k * m.rhs_k * m.rhs_k);
   s.lprop_binding_term = m.lprop_binding_term;
