@@ -192,3 +192,33 @@ class DeviceEnsemble:
         if self.dist:
             self.dist.all_reduce(acc)
         return acc.double() / max(1, self.step)
+
+
+def run_concurrently(ensembles, nsteps, store=False):
+    """Advance several independent device ensembles (e.g. one per dataset / burst) ``nsteps`` steps each, every
+    ensemble on its own CUDA stream with the launches interleaved step by step, so that small ensembles --
+    which are latency-bound, a few warps each -- share the GPU instead of queueing behind one another.
+    Returns a list of (chain, lnprob) per ensemble when ``store`` (else None)."""
+    import torch
+    streams = [torch.cuda.Stream(device=e.device) for e in ensembles]
+    for e, st in zip(ensembles, streams):
+        st.wait_stream(torch.cuda.current_stream(e.device))
+    out = []
+    if store:
+        for e in ensembles:
+            out.append((torch.empty((nsteps, e.nwalkers, e.ndim), dtype=torch.float64, device=e.device),
+                        torch.empty((nsteps, e.nwalkers), dtype=torch.float64, device=e.device)))
+    for it in range(nsteps):
+        for k, (e, st) in enumerate(zip(ensembles, streams)):
+            with torch.cuda.stream(st):
+                for split in (0, 1):
+                    e.half_step(e.coords, e.lnp, e.mine[split], e.halves[1 - split], e.a, e.seed, 2 * e.step + split,
+                                e.accepted)
+                    e._gather(split)
+                e.step += 1
+                if store:
+                    out[k][0][it].copy_(e.coords)
+                    out[k][1][it].copy_(e.lnp)
+    for e, st in zip(ensembles, streams):
+        torch.cuda.current_stream(e.device).wait_stream(st)
+    return out if store else None

@@ -71,5 +71,33 @@ def main():
         summary(n, res.get_chain(), 1000)
 
 
+def concurrent_config1(data):
+    """configs[1] with the three datasets' chains advancing side by side (one stream each)."""
+    import torch
+    from magprop_b200 import _capi as A
+    from magprop_b200.engine import Likelihood, time_grid
+    from magprop_b200.sampler import DeviceEnsemble, run_concurrently
+    from magprop_b200.synthetic.mcmc_eqns import lower, upper
+    liks, ens = [], []
+    for i, n in enumerate(("Classic", "Sloped", "Stuttering")):
+        lk = Likelihood(A.script_model_spec(), time_grid(None), *data[n], lower, upper)
+        e = DeviceEnsemble.from_likelihood(lk, 256, 6, a=2.0, seed=3)
+        e.initialise(S.initial_ball(n, 256, rng=np.random.RandomState(3)))
+        liks.append(lk); ens.append(e)
+    run_concurrently(ens, 5)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = run_concurrently(ens, 2000, store=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    print(f"configs[1], three datasets side by side: {dt:.2f} s for {3 * 256 * 2000} evaluations ({3 * 256 * 2000 / dt:.3e} evals/s)")
+    for (chain, lnp), n in zip(res, ("Classic", "Sloped", "Stuttering")):
+        print(f"  {n}: final mean lnprob {lnp[-1].mean().item():.2f}, median {np.round(np.median(chain[1000:].cpu().numpy().reshape(-1, 6), axis=0), 3).tolist()}")
+    for lk in liks:
+        lk.close()
+
+
 if __name__ == "__main__":
     main()
+    g_ = np.load(os.path.join(ROOT, "tests", "golden", "lnprob_script.npz"))
+    concurrent_config1({n: (g_[f"{n}_x"], g_[f"{n}_y"], g_[f"{n}_yerr"]) for n in ("Classic", "Sloped", "Stuttering")})
