@@ -967,10 +967,10 @@ static bool breakup_sliding_block_y(const Spec& sp, const Walker& w, const Stage
 // per kink on the synthetic truths), and what error it lets through is the LARGEST contribution to the
 // global error (measured: landing on the kinks lowers the error in omega 5-40x at equal rtol).  So when
 // the regime bits of a trial step's two end points differ, the crossing is located -- the margin of the
-// bit that flipped at the two ends, two regula-falsi refinements and a final secant estimate, with the
+// bit that flipped at the two ends, one regula-falsi refinement and a final secant estimate, with the
 // state interpolated linearly (omega moves by < 1e-3 over a step here; the margin is dominated by the
-// disc mass and is close to linear over a step, so this lands within ~1e-5 of the step) -- and the step
-// is retried to END on the kink.  Three disc-mass evaluations, no right-hand-side evaluations; kept this
+// disc mass and is close to linear over a step, so this lands within ~1e-3 of the step) -- and the step
+// is retried to END on the kink.  Two disc-mass evaluations, no right-hand-side evaluations; kept this
 // small because in an ensemble that is spread out the lanes of a warp meet their kinks on different
 // trips and each call runs with one active lane.
 // Returns the fraction of the step at which the kink sits, or -1.
@@ -992,8 +992,7 @@ static double locate_kink(const Spec& sp, const Walker& w, double t, double h, d
   disc_stages<1>(w, &t, &d);
   double a = 0.0, b = 1.0, fa = margin(0.0, d.qa * sp.g_qa), fb = margin(1.0, qa_end);
   if (!(fa * fb < 0.0)) return -1.0;              // also NaN
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
+  {   // one regula-falsi refinement (a second one: +0 accuracy at the landing tolerance, -3..5 % on spread ensembles)
     const double th = (a * fb - b * fa) / (fb - fa);
     const double tt = fma(th, h, t);
     disc_stages<1>(w, &tt, &d);
