@@ -105,6 +105,11 @@ struct DataView {
 };
 
 // ---- the disc-mass kernel function S(u) ----------------------------------
+// Loads of the dataset / node program.  The kernels stage them in shared memory when they fit (then these are
+// LDS through a generic pointer) and leave them in global memory otherwise, so a plain generic load is used
+// rather than ld.global.nc.
+MP_HD double ldd(const double* p) { return *p; }
+
 MP_HD double ldg(const double* p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);
@@ -1469,7 +1474,7 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
   const int Nn = dv.n_nodes;
   n_rhs = 0;
   if (Nn <= 0) return 0.0;
-  const double t_end = ldg(dv.node_t + (Nn - 1));
+  const double t_end = ldd(dv.node_t + (Nn - 1));
   Integrator in;
   in.status = kWalkerOk;
   in.n_rhs = 0;
@@ -1496,13 +1501,13 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
     for (;;) {
       bool step = false;
       if (integrate && !deferred && jn < c1) {
-        double tn = ldg(dv.node_t + jn);
+        double tn = ldd(dv.node_t + jn);
         if (tn <= in.t) {
           const double ihs = 1.0 / in.hs;
           do {
             buf[(jn - c0) * bstride] = dense_eval_r(in, tn, ihs);
             if (++jn >= c1) break;
-            tn = ldg(dv.node_t + jn);
+            tn = ldd(dv.node_t + jn);
           } while (tn <= in.t);
         }
         if (jn < c1) {
@@ -1540,7 +1545,7 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
         __syncwarp();
         const int j = c0 + lane;
         if (j < c1) {
-          const double tn = ldg(dv.node_t + j);
+          const double tn = ldd(dv.node_t + j);
           const double v = buf[lane * bstride + (src - lane)];         // column of lane `src`, row `lane`
           const double om = sw->bad ? ((tn == dv.t_start) ? sw->omega0 : NAN) : (STIFF ? v : rsqrt_pos(v));
           const double M = sw->bad ? ((tn == dv.t_start) ? sw->M_init : NAN)
@@ -1563,7 +1568,7 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
     // ---- phase B
     for (int j = c0; j < c1; ++j) {
       const double v = buf[(j - c0) * bstride];
-      const double tn = ldg(dv.node_t + j);
+      const double tn = ldd(dv.node_t + j);
       double M, om;
       if (w.bad) {
         M = (tn == dv.t_start) ? w.M_init : NAN;
@@ -1584,17 +1589,17 @@ MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w
       } else {
         while (idat < dv.n_data) {
           const int lo = dv.dat_lo[idat];
-          const double dx = ldg(dv.dat_dx + idat);
+          const double dx = ldd(dv.dat_dx + idat);
           const int hi = lo + (dx != 0.0 ? 1 : 0);
           if (hi > j) break;
           double mod;
           if (dx == 0.0) {
             mod = L.tot;                                   // datum sits on a grid node
           } else {
-            mod = fma(L.tot - Lprev, ldg(dv.dat_w + idat), Lprev);   // np.interp: slope*(x-x_lo)+y_lo
+            mod = fma(L.tot - Lprev, ldd(dv.dat_w + idat), Lprev);   // np.interp: slope*(x-x_lo)+y_lo
           }
           if (MODE == kModeLnprob) {
-            const double r = fma(-mod, ldg(dv.dat_c + idat), ldg(dv.dat_ys + idat));   // (y - mod/1e50)/yerr
+            const double r = fma(-mod, ldd(dv.dat_c + idat), ldd(dv.dat_ys + idat));   // (y - mod/1e50)/yerr
             chi2 = fma(r, r, chi2);
           } else {
             out[(dat_orig ? dat_orig[idat] : idat) * ostride] = mod * 1.0e-50;

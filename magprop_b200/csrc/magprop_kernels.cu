@@ -73,6 +73,30 @@ __device__ __forceinline__ void stage_theta(const double* __restrict__ theta, in
   __syncthreads();
 }
 
+// The dataset a block works against -- node times and, per datum, y/yerr, 1e-50/yerr, x - t_lo, the
+// interpolation weight and the lower-node index -- staged in shared memory when it fits the budget below
+// (the synthetic datasets take 2.2 KB; a 1944-point burst stays in global memory behind L1).
+constexpr int kDataSmemDoubles = 768;      // 6 KB per block
+__device__ __forceinline__ bool stage_data(const DataView& g, DataView& s, double* buf, int nthreads) {
+  const int Nn = g.n_nodes, D = g.n_data;
+  const int need = Nn + 4 * D + (D + 1) / 2;
+  if (need > kDataSmemDoubles) return false;
+  double* p = buf;
+  double* nt = p; p += Nn;
+  double* ys = p; p += D;
+  double* c = p; p += D;
+  double* dx = p; p += D;
+  double* w = p; p += D;
+  int* lo = reinterpret_cast<int*>(p);
+  for (int i = threadIdx.x; i < Nn; i += nthreads) nt[i] = g.node_t[i];
+  for (int i = threadIdx.x; i < D; i += nthreads) {
+    ys[i] = g.dat_ys[i]; c[i] = g.dat_c[i]; dx[i] = g.dat_dx[i]; w[i] = g.dat_w[i]; lo[i] = g.dat_lo[i];
+  }
+  s = g;
+  s.node_t = nt; s.dat_ys = ys; s.dat_c = c; s.dat_dx = dx; s.dat_w = w; s.dat_lo = lo;
+  return true;
+}
+
 #ifndef MP_MIN_BLOCKS_32
 #define MP_MIN_BLOCKS_32 16
 #endif
@@ -84,7 +108,8 @@ __device__ __forceinline__ void stage_theta(const double* __restrict__ theta, in
 // `have` = false: this lane has no walker; it still walks through evaluate_walker as a bystander
 // because the warp votes there need every lane.
 template <int MODE, int BLOCK, bool STIFF>
-__device__ __forceinline__ bool eval_one(const KernelArgs& a, bool have, int w, const double* th, double* s_buf, void* warp_scratch) {
+__device__ __forceinline__ bool eval_one(const KernelArgs& a, const DataView& dv, bool have, int w, const double* th, double* s_buf,
+                                         void* warp_scratch) {
   int st = kWalkerOk, nr = 0;
   double result = -INFINITY;
   const bool rejected = have && a.prior_enabled && !prior_accepts(th, a.ndim, a.lower, a.upper);
@@ -94,16 +119,16 @@ __device__ __forceinline__ bool eval_one(const KernelArgs& a, bool have, int w, 
     double pars[6], dipeff, propeff, f_beam;
     unpack_theta(a.sp, th, a.ndim, pars, dipeff, propeff, f_beam);
     Walker wk;
-    walker_setup(a.sp, pars, dipeff, propeff, f_beam, a.dv.t_start, wk);
+    walker_setup(a.sp, pars, dipeff, propeff, f_beam, dv.t_start, wk);
     double* out = nullptr;
     double* state = nullptr;
     if (MODE == kModeCurves) {
-      out = a.out + (size_t)w * 3 * a.dv.n_nodes;
-      state = a.state ? a.state + (size_t)w * 2 * a.dv.n_nodes : nullptr;
+      out = a.out + (size_t)w * 3 * dv.n_nodes;
+      state = a.state ? a.state + (size_t)w * 2 * dv.n_nodes : nullptr;
     } else if (MODE == kModeModelAtData) {
-      out = a.out + (size_t)w * a.dv.n_data;
+      out = a.out + (size_t)w * dv.n_data;
     }
-    const double chi2 = evaluate_walker<MODE, NodeBuf<MODE>::n, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK, st, nr,
+    const double chi2 = evaluate_walker<MODE, NodeBuf<MODE>::n, STIFF>(a.sp, dv, wk, live, s_buf + threadIdx.x, BLOCK, st, nr,
                                                           out, state, 1, a.dat_orig, warp_scratch);
     if (!STIFF && (st & kWalkerDeferred)) return true;
     if (live && MODE == kModeLnprob) {
@@ -131,6 +156,9 @@ eval_kernel(const __grid_constant__ KernelArgs a) {
   __shared__ double s_buf[NodeBuf<MODE>::n * BLOCK];
   __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
   __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];   // per-warp broadcast slot (curve output)
+  __shared__ double s_data[MODE == kModeCurves ? 1 : kDataSmemDoubles];
+  DataView dv = a.dv;
+  if (MODE != kModeCurves) stage_data(a.dv, dv, s_data, BLOCK);       // (stage_theta's barrier covers it)
   const int lpw = (MODE == kModeCurves && a.lanes_per_walker > 1) ? a.lanes_per_walker : 1;
   stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta, a.order, lpw);
   const int slot = blockIdx.x * BLOCK + threadIdx.x;
@@ -138,7 +166,7 @@ eval_kernel(const __grid_constant__ KernelArgs a) {
   const bool have = (i < a.W) && (slot % lpw == 0);
   const int w = (a.order && have) ? a.order[i] : i;
   void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
-  if (eval_one<MODE, BLOCK, false>(a, have, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch))
+  if (eval_one<MODE, BLOCK, false>(a, dv, have, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch))
     a.queue[atomicAdd(a.queue_count, 1)] = w;
 }
 
@@ -161,7 +189,7 @@ __global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) eval_s
   const int w = have ? a.queue[i] : 0;
   double th[MP_MAX_NDIM];
   for (int d = 0; d < a.ndim; ++d) th[d] = a.theta[(size_t)w * a.ndim + d];
-  eval_one<MODE, BLOCK, true>(a, have, w, th, s_buf, scratch);
+  eval_one<MODE, BLOCK, true>(a, a.dv, have, w, th, s_buf, scratch);
 }
 
 // ---- counter-based RNG: Philox4x32-10 (Salmon et al. 2011) -------------------
