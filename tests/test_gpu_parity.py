@@ -10,6 +10,8 @@ relative, lnprior accept/reject bit-exact):
     node/walker (default odeint is itself up to 1e-5 off at
     the propeller switch-on).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -107,6 +109,27 @@ def test_live_oracle_four_truths(built):
         slack = TOL_REF * np.abs(dflt[1:2]) + 1.5 * np.abs(dflt[1:] - tight[1:])
         assert (np.abs(out[i] - dflt[1:]) <= slack).all()
     lk.close()
+
+
+def test_live_oracle_fresh_prior_draws(built, golden):
+    """Walkers the tolerances were NOT calibrated on: 96 fresh draws (a third prior-uniform, the rest spread around
+    the Sloped and Stuttering truths) against the converged oracle run now on the host cores."""
+    from multiprocessing import get_context
+    g = golden["lnprob_script"]
+    rng = np.random.RandomState(20240229)
+    for name in ("Sloped", "Stuttering"):
+        theta = np.concatenate([rng.uniform(O.SCRIPT_LOWER, O.SCRIPT_UPPER, size=(16, 6)),
+                                np.clip(O.SYNTH_TRUTHS_LOG[name] + 0.1 * rng.randn(32, 6), O.SCRIPT_LOWER, O.SCRIPT_UPPER)])
+        x, y, ye = g[f"{name}_x"], g[f"{name}_y"], g[f"{name}_yerr"]
+        lk = script_lik(g, name)
+        lnp, st, _ = lk.lnprob(theta, return_info=True)
+        lk.close()
+        with get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+            want = O.lnprob_batch(theta, x, y, ye, O.script_spec(), O.SCRIPT_LOWER, O.SCRIPT_UPPER, tight=True, pool=pool)
+        ok = np.isfinite(want) & ((st & A.WALKER_INTEGRATOR_FAIL) == 0)
+        assert ok.sum() >= 40
+        assert relerr(lnp[ok], want[ok]).max() < TOL_TIGHT
+        assert not np.isnan(lnp).any()
 
 
 def test_packaged_lnprob_6_to_9_parameters(built, golden):
