@@ -121,3 +121,38 @@ def test_device_half_step_matches_numpy_double(built, golden):
     assert 0 < acc.sum() < n * nsteps
     assert np.isfinite(lnp).all()
     lk.close()
+
+
+@pytest.mark.gpu
+def test_run_concurrently_matches_sequential_runs(built, golden):
+    """Three datasets' ensembles advanced side by side (one stream each) give the chains of three separate runs."""
+    import torch
+    from magprop_b200 import _capi as A
+    from magprop_b200.engine import Likelihood, time_grid
+    from magprop_b200.sampler import run_concurrently
+    from oracle import magprop_oracle as O
+    g = golden["lnprob_script"]
+    names = ("Classic", "Sloped", "Stuttering")
+
+    def make():
+        liks, ens = [], []
+        for k, n in enumerate(names):
+            lk = Likelihood(A.script_model_spec(), time_grid(None), g[f"{n}_x"], g[f"{n}_y"], g[f"{n}_yerr"],
+                            O.SCRIPT_LOWER, O.SCRIPT_UPPER)
+            e = DeviceEnsemble.from_likelihood(lk, 64, 6, a=2.0, seed=5 + k)
+            e.initialise(O.SYNTH_TRUTHS_LOG[n] + 1e-3 * np.random.RandomState(k).randn(64, 6))
+            liks.append(lk); ens.append(e)
+        return liks, ens
+
+    liks, ens = make()
+    seq = [e.run(8, store=True) for e in ens]
+    torch.cuda.synchronize()
+    for lk in liks:
+        lk.close()
+    liks, ens = make()
+    par = run_concurrently(ens, 8, store=True)
+    torch.cuda.synchronize()
+    for (c0, l0), (c1, l1), e in zip(seq, par, ens):
+        assert torch.equal(c0, c1) and torch.equal(l0, l1) and e.step == 8
+    for lk in liks:
+        lk.close()
