@@ -156,3 +156,20 @@ def test_run_concurrently_matches_sequential_runs(built, golden):
         assert torch.equal(c0, c1) and torch.equal(l0, l1) and e.step == 8
     for lk in liks:
         lk.close()
+
+
+@pytest.mark.gpu
+def test_nccl_sharded_ensemble_matches_single_gpu(built):
+    """Two ranks over NCCL, each moving half of every half-ensemble and all-gathering the updates, reproduce the
+    single-GPU chain bit for bit (counter-based RNG, no cross-rank state).  Needs two visible GPUs."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tools", "check_dist_mcmc.py")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("sharded == single: True") == 2
