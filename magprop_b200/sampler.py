@@ -118,6 +118,8 @@ class DeviceEnsemble:
         self.half_step, self.nwalkers, self.ndim, self.a, self.seed = half_step, nwalkers, ndim, float(a), int(seed)
         self.device = torch.device(device)
         self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
+        # gloo (the CPU tests) needs a separate send buffer; NCCL gathers in place
+        self.inplace_gather = bool(self.dist) and self.dist.get_backend() == "nccl"
         self.rank = self.dist.get_rank() if self.dist else 0
         self.world = self.dist.get_world_size() if self.dist else 1
         half = nwalkers // 2
@@ -162,13 +164,18 @@ class DeviceEnsemble:
         """All-gather this rank's updated rows of half `split` into the replicated arrays."""
         if not self.dist:
             return
-        t, half = self.torch, self.nwalkers // 2
+        half = self.nwalkers // 2
         lo, hi = self.my_rows[split]
         base = split * half
-        send_c = self.coords[lo:hi].clone()
-        send_l = self.lnp[lo:hi].clone()
-        self.dist.all_gather_into_tensor(self.coords[base:base + half], send_c)
-        self.dist.all_gather_into_tensor(self.lnp[base:base + half], send_l)
+        if self.inplace_gather:
+            # NCCL's in-place all-gather: this rank's rows already sit at their place in the output
+            self.dist.all_gather_into_tensor(self.coords[base:base + half], self.coords[lo:hi])
+            self.dist.all_gather_into_tensor(self.lnp[base:base + half], self.lnp[lo:hi])
+        else:
+            send_c = self.coords[lo:hi].clone()
+            send_l = self.lnp[lo:hi].clone()
+            self.dist.all_gather_into_tensor(self.coords[base:base + half], send_c)
+            self.dist.all_gather_into_tensor(self.lnp[base:base + half], send_l)
 
     def run(self, nsteps, store=False):
         """nsteps stretch-move steps (2 half-steps each).  Returns the chain

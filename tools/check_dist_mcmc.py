@@ -16,7 +16,7 @@ os.environ.setdefault("NCCL_DEBUG", "NONE")
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 g = np.load(os.path.join(ROOT, "tests", "golden", "lnprob_script.npz"))
 lk = Likelihood(A.script_model_spec(), time_grid(None), g["Humped_x"], g["Humped_y"], g["Humped_yerr"], lower, upper, device=local)
-n = 4096
+n = int(os.environ.get("NWALK", 4096))
 p0 = truths["Humped"] + 1e-2 * np.random.RandomState(4).randn(n, 6)
 sharded = DeviceEnsemble.from_likelihood(lk, n, 6, a=2.0, seed=17, dist=dist)
 sharded.initialise(p0)
