@@ -49,7 +49,7 @@ with open(os.path.join(ROOT, "profiles", "r01_executed.json")) as _f:
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ensembles", type=int, default=1184,
@@ -314,8 +314,8 @@ def run_ours(args):
         "mean_rhs_per_eval": mean_nrhs, "hbm_bytes_per_eval": 48 + 8 + 4,
         "survey_8d_convention": {
             "note": "SURVEY.md 8(d) counts the reference's formulation (440 flop per RHS: generic pow/tanh/sqrt); "
-                    "the kernel's closed-form disc mass and hoisted constants need about a third of that, so this "
-                    "figure can exceed the hardware peak and is reported for comparison only",
+                    "the kernel's closed-form disc mass and hoisted constants need about a quarter of that, so this "
+                    "figure exceeds the hardware peak and is reported for comparison only",
             "flop_per_eval": flop_per_eval, "tflops": achieved, "frac": achieved / peak if peak else None},
     }
     if rank == 0:
