@@ -26,6 +26,7 @@ namespace mp {
 #define MP_KNB 16
 #endif
 constexpr int kNB = MP_KNB;  // nodes buffered per thread between phase A and phase B
+constexpr int kResumeLen = kResumeDoubles + kNB;   // one hand-over record (see evaluate_walker)
 // curve output hands one node to each lane of the warp in phase B, so it buffers a full warp's worth
 template <int MODE> struct NodeBuf { static constexpr int n = (MODE == kModeCurves) ? 32 : kNB; };
 
@@ -47,6 +48,7 @@ struct KernelArgs {
   int lanes_per_walker; // curve output: one walker per this many lanes (1, 2, .. 32), see launch_eval
   int* queue;           // [W] walkers deferred to the stiff launch
   int* queue_count;     // [1]
+  double* resume;       // [queue capacity][kResumeLen] hand-over records of the deferred walkers, or null
 };
 
 // Coalesced load of this block's walker parameters into shared memory
@@ -109,7 +111,7 @@ __device__ __forceinline__ bool stage_data(const DataView& g, DataView& s, doubl
 // because the warp votes there need every lane.
 template <int MODE, int BLOCK, bool STIFF>
 __device__ __forceinline__ bool eval_one(const KernelArgs& a, const DataView& dv, bool have, int w, const double* th, double* s_buf,
-                                         void* warp_scratch) {
+                                         void* warp_scratch, ResumeSink* sink = nullptr, const double* rec_in = nullptr) {
   int st = kWalkerOk, nr = 0;
   double result = -INFINITY;
   const bool rejected = have && a.prior_enabled && !prior_accepts(th, a.ndim, a.lower, a.upper);
@@ -129,7 +131,9 @@ __device__ __forceinline__ bool eval_one(const KernelArgs& a, const DataView& dv
       out = a.out + (size_t)w * dv.n_data;
     }
     const double chi2 = evaluate_walker<MODE, NodeBuf<MODE>::n, STIFF>(a.sp, dv, wk, live, s_buf + threadIdx.x, BLOCK, st, nr,
-                                                          out, state, 1, a.dat_orig, warp_scratch);
+                                                          out, state, 1, a.dat_orig, warp_scratch,
+                                                          MODE == kModeCurves ? nullptr : sink,
+                                                          MODE == kModeCurves ? nullptr : rec_in);
     if (!STIFF && (st & kWalkerDeferred)) return true;
     if (live && MODE == kModeLnprob) {
       double ll = -0.5 * chi2;                     // mcmc_eqns.py:25
@@ -166,8 +170,10 @@ eval_kernel(const __grid_constant__ KernelArgs a) {
   const bool have = (i < a.W) && (slot % lpw == 0);
   const int w = (a.order && have) ? a.order[i] : i;
   void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
-  if (eval_one<MODE, BLOCK, false>(a, dv, have, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch))
-    a.queue[atomicAdd(a.queue_count, 1)] = w;
+  // (a deferred walker claims its queue slot -- and leaves its hand-over record there -- inside evaluate_walker)
+  ResumeSink sink{(MODE != kModeCurves && a.resume) ? a.queue_count : nullptr, a.resume, -1};
+  if (eval_one<MODE, BLOCK, false>(a, dv, have, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch, &sink))
+    a.queue[sink.count ? sink.slot : atomicAdd(a.queue_count, 1)] = w;
 }
 
 // Second launch: the walkers bucketed as stiff, with the implicit integrator available.
@@ -189,7 +195,8 @@ __global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) eval_s
   const int w = have ? a.queue[i] : 0;
   double th[MP_MAX_NDIM];
   for (int d = 0; d < a.ndim; ++d) th[d] = a.theta[(size_t)w * a.ndim + d];
-  eval_one<MODE, BLOCK, true>(a, a.dv, have, w, th, s_buf, scratch);
+  eval_one<MODE, BLOCK, true>(a, a.dv, have, w, th, s_buf, scratch, nullptr,
+                              (MODE != kModeCurves && a.resume && have) ? a.resume + (size_t)i * kResumeLen : nullptr);
 }
 
 // ---- counter-based RNG: Philox4x32-10 (Salmon et al. 2011) -------------------
@@ -235,7 +242,8 @@ struct StretchArgs {
 // fused with the likelihood so a half-step is one launch (plus the stiff-bucket launch, which
 // finds an empty queue for ensembles near the synthetic truths).  Returns true when deferred.
 template <int BLOCK, bool STIFF>
-__device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int me, double* s_buf) {
+__device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int me, double* s_buf, ResumeSink* sink = nullptr,
+                                            const double* rec_in = nullptr) {
   const KernelArgs& a = s.k;
   const int ndim = a.ndim;
   // counter = (step, walker); two Philox blocks give u_z, u_partner, u_accept
@@ -266,7 +274,7 @@ __device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int
     Walker wk;
     walker_setup(a.sp, pars, dipeff, propeff, f_beam, a.dv.t_start, wk);
     const double chi2 = evaluate_walker<kModeLnprob, kNB, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK,
-                                                                 st, nr, nullptr, nullptr, 1, nullptr, nullptr);
+                                                                 st, nr, nullptr, nullptr, 1, nullptr, nullptr, sink, rec_in);
     if (!STIFF && (st & kWalkerDeferred)) return true;
     if (live) {
       double ll = -0.5 * chi2;
@@ -293,7 +301,9 @@ stretch_kernel(const __grid_constant__ StretchArgs s) {
   const int i = blockIdx.x * BLOCK + threadIdx.x;
   const bool have = i < s.n_active;
   const int me = have ? s.active[i] : s.active[0];
-  if (stretch_one<BLOCK, false>(s, have, me, s_buf)) s.k.queue[atomicAdd(s.k.queue_count, 1)] = me;
+  ResumeSink sink{s.k.resume ? s.k.queue_count : nullptr, s.k.resume, -1};
+  if (stretch_one<BLOCK, false>(s, have, me, s_buf, &sink))
+    s.k.queue[sink.count ? sink.slot : atomicAdd(s.k.queue_count, 1)] = me;
 }
 
 template <int BLOCK>
@@ -303,7 +313,8 @@ __global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) stretc
   const int i = blockIdx.x * BLOCK + threadIdx.x;
   if (blockIdx.x * BLOCK >= n) return;
   const bool have = i < n;
-  stretch_one<BLOCK, true>(s, have, have ? s.k.queue[i] : s.active[0], s_buf);
+  stretch_one<BLOCK, true>(s, have, have ? s.k.queue[i] : s.active[0], s_buf, nullptr,
+                           (s.k.resume && have) ? s.k.resume + (size_t)i * kResumeLen : nullptr);
 }
 
 // ---- the coupled right-hand side, as ODEs()/odes() return it -----------------------
@@ -416,6 +427,8 @@ struct mp_handle {
     int* queue = nullptr;        // walkers deferred to the stiff launch
     int* queue_count = nullptr;
     size_t cap_queue = 0;
+    double* resume = nullptr;    // hand-over records, one per queue slot
+    size_t cap_resume = 0;
     // walker bucketing (mp_set_bucketing): sort keys / walker ids (double-buffered) and CUB's scratch
     unsigned *key_in = nullptr, *key_out = nullptr;
     int *id_in = nullptr, *id_out = nullptr;
@@ -518,7 +531,7 @@ extern "C" void mp_destroy(mp_handle* h) {
   cudaFree(h->s_theta); cudaFree(h->s_out); cudaFree(h->s_state); cudaFree(h->s_lnp);
   cudaFree(h->s_status); cudaFree(h->s_nrhs);
   for (auto& L : h->lanes) {
-    cudaFree(L.queue); cudaFree(L.queue_count);
+    cudaFree(L.queue); cudaFree(L.queue_count); cudaFree(L.resume);
     cudaFree(L.key_in); cudaFree(L.key_out); cudaFree(L.id_in); cudaFree(L.id_out); cudaFree(L.sort_tmp);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
@@ -571,8 +584,10 @@ static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream
   mp_handle::Lane& L = h->lanes[lane];
   int rc = ensure(&L.queue, &L.cap_queue, (size_t)W);
   if (rc) return rc;
+  if ((rc = ensure(&L.resume, &L.cap_resume, (size_t)W * kResumeLen))) return rc;
   a.queue = L.queue;
   a.queue_count = L.queue_count;
+  a.resume = L.resume;
   MP_CUDA(cudaMemsetAsync(L.queue_count, 0, sizeof(int), stream));
   return MP_OK;
 }
@@ -642,6 +657,7 @@ static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lan
   int rc = prepare_queue(h, a, a.W, stream, lane);
   if (rc) return rc;
   if (a.sp.bucciantini) {
+    a.resume = nullptr;                                  // every walker starts in the implicit kernel
     queue_all_kernel<<<(a.W + 255) / 256, 256, 0, stream>>>(a.queue, a.queue_count, a.W);
     eval_stiff_kernel<MODE, 64><<<(a.W + 63) / 64, 64, 0, stream>>>(a);
     MP_CUDA(cudaGetLastError());
@@ -906,6 +922,7 @@ extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_ln
   if (n_active == 0) return MP_OK;
   if ((rc = prepare_queue(h, s.k, n_active, (cudaStream_t)stream))) return rc;
   if (s.k.sp.bucciantini) {
+    s.k.resume = nullptr;
     queue_all_kernel<<<(n_active + 255) / 256, 256, 0, (cudaStream_t)stream>>>(s.k.queue, s.k.queue_count, n_active, d_active);
     stretch_stiff_kernel<64><<<(n_active + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s);
     MP_CUDA(cudaGetLastError());

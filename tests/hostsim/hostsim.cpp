@@ -31,11 +31,17 @@ static double evaluate_two_pass(const Spec& sp, const DataView& dv, const Walker
                                 double* out, double* state, const int* dat_orig) {
   int st1 = st, nr1 = 0;
   double r = 0.0;
+  double rec[kResumeDoubles + 64];
+  int count = 0;
+  ResumeSink sink{&count, rec, -1};
+  const bool handover = MODE != kModeCurves && !sp.bucciantini;   // as the kernels: curves restart, so does a Bucciantini spec
   if (sp.bucciantini) st1 |= kWalkerDeferred;      // launch_eval routes such a spec to the implicit variant
-  else r = evaluate_walker<MODE, 64, false>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr);
+  else r = evaluate_walker<MODE, 64, false>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr,
+                                            handover ? &sink : nullptr);
   if (st1 & kWalkerDeferred) {
     st1 = st; nr1 = 0;
-    r = evaluate_walker<MODE, 64, true>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr);
+    r = evaluate_walker<MODE, 64, true>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr, nullptr,
+                                        handover ? rec : nullptr);
   }
   st = st1; nr = nr1;
   return r;
