@@ -132,6 +132,37 @@ def test_live_oracle_fresh_prior_draws(built, golden):
         assert not np.isnan(lnp).any()
 
 
+def _tight_curve(args):
+    p, kw = args
+    return O.model(p, O.script_spec(**kw), tight=True)
+
+
+def test_live_oracle_model_knobs(built):
+    """The model's keyword knobs (funcs.py:146-147: n, alpha, cs7, k, efficiencies) away from their defaults -- steeper and
+    shallower propeller switch, a different light-cylinder cap (it moves the kink the integrator lands on), a different
+    viscous time -- against the converged oracle run now."""
+    from multiprocessing import get_context
+    rng = np.random.RandomState(77)
+    combos = [dict(n=1.0), dict(n=50.0), dict(k=0.5), dict(k=0.99, n=3.0), dict(alpha=0.03), dict(cs7=3.0, n=20.0),
+              dict(dipeff=0.3, propeff=0.7, f_beam=12.0, k=0.7)]
+    pars = np.array([O.SYNTH_TRUTHS[n_] for n_ in ("Humped", "Classic", "Sloped", "Stuttering")])
+    pars = np.concatenate([pars, pars * (1.0 + 0.3 * rng.uniform(-1, 1, pars.shape))])
+    idx = np.arange(0, 10001, 100)
+    jobs = [(p, kw) for kw in combos for p in pars]
+    with get_context("fork").Pool(min(16, os.cpu_count() or 1)) as pool:
+        want = pool.map(_tight_curve, jobs, chunksize=1)
+    j = 0
+    for kw in combos:
+        lk = Likelihood(A.script_model_spec(unlog=False, **kw), time_grid(None))
+        out, st = lk.curves(pars, node_stride=100)
+        lk.close()
+        for i in range(len(pars)):
+            tight = want[j]; j += 1
+            if isinstance(tight, str) or (st[i] & A.WALKER_INTEGRATOR_FAIL):
+                continue
+            assert_curves_close(out[i], tight[1:][:, idx])
+
+
 def test_packaged_lnprob_6_to_9_parameters(built, golden):
     g = golden["lnprob_packaged"]
     for th, want in zip(g["theta"], g["ref_lnprob"]):
