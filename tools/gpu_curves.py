@@ -4,7 +4,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import numpy as np, torch
 from magprop_b200 import _capi as A
 from magprop_b200.engine import Likelihood, time_grid
-from oracle import magprop_oracle as O
+from magprop_b200.synthetic.mcmc_eqns import lower as _LO, upper as _HI
+from magprop_b200.synthetic.synth_mcmc import truths as _TR
+
+
+class O:      # the constants these tools need, from the package (the oracle is test infrastructure)
+    SCRIPT_LOWER, SCRIPT_UPPER, SYNTH_TRUTHS_LOG = _LO, _HI, _TR
 
 W = int(os.environ.get("W", 16384))
 rng = np.random.RandomState(5)

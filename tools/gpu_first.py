@@ -4,7 +4,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.ins
 import numpy as np, torch
 from magprop_b200 import _capi as A
 from magprop_b200.engine import Likelihood, time_grid, fp64_peak_tflops
-from oracle import magprop_oracle as O
+from magprop_b200.synthetic.mcmc_eqns import lower as _LO, upper as _HI
+from magprop_b200.synthetic.synth_mcmc import truths as _TR
+
+
+class O:      # the constants these tools need, from the package (the oracle is test infrastructure)
+    SCRIPT_LOWER, SCRIPT_UPPER, SYNTH_TRUTHS_LOG = _LO, _HI, _TR
 print("fp64 peak TFLOP/s:", fp64_peak_tflops(0))
 g = np.load(os.path.join(ROOT, "tests/golden/lnprob_script.npz"))
 grid = time_grid(None)
