@@ -80,30 +80,84 @@ def workload_config(args):
 
 
 # ------------------------------------------------------------------------------------ CPU legs
-def _cpu_task(a):
+REF_ROOT = "/root/reference"
+
+
+def reference_present():
+    return os.path.exists(os.path.join(REF_ROOT, "code", "synthetic_datasets", "funcs.py"))
+
+
+_REF = None
+
+
+def _ref_modules():
+    """The reference's own script-variant modules, imported unmodified from /root/reference (present in the
+    build container only -- a Python tree cannot travel to the GPU box)."""
+    global _REF
+    if _REF is None:
+        sys.dont_write_bytecode = True
+        sys.path.insert(0, os.path.join(REF_ROOT, "code", "synthetic_datasets"))
+        import warnings
+        warnings.filterwarnings("ignore")
+        import funcs as ref_funcs, mcmc_eqns as ref_mc      # noqa: E401
+        _REF = (ref_funcs, ref_mc)
+    return _REF
+
+
+def _cpu_task_reference(a):
+    """The reference's lnprob (mcmc_eqns.py:52-81) through its own lnprior and model_lum; only :22
+    (`mod == 'flag'` on an ndarray, a ValueError under numpy >= 2) and the lines around it are restated."""
+    ref_funcs, ref_mc = _ref_modules()
+    theta, x, y, yerr = a
+    lp = ref_mc.lnprior(theta)
+    if not np.isfinite(lp):
+        return -np.inf
+    arr = np.array(theta)
+    arr[2:] = 10.0 ** arr[2:]
+    mod = ref_funcs.model_lum(arr, xdata=x)
+    if isinstance(mod, str):
+        return -np.inf
+    ll = -0.5 * np.sum(((y - mod) / yerr) ** 2.0)
+    return ll + lp if np.isfinite(ll) else -np.inf
+
+
+def _cpu_task_port(a):
     from oracle import magprop_oracle as O
     theta, x, y, yerr = a
     return O.lnprob(theta, x, y, yerr, O.script_spec(), O.SCRIPT_LOWER, O.SCRIPT_UPPER)
 
 
+def cpu_kind():
+    return "reference" if reference_present() else "port"
+
+
 def cpu_throughput(n_evals, seed=0, procs=None):
-    """Oracle lnprob (the reference's odeint path, restated) over a Pool, as the
-    reference's own Pool.map does (synth_mcmc.py:178-185)."""
+    """The reference's odeint path over a Pool, as its own Pool.map does (synth_mcmc.py:178-185): the unmodified
+    reference functions when /root/reference is present, else the oracle's restatement of them."""
     from multiprocessing import get_context
-    from oracle import magprop_oracle as O
+    from magprop_b200.synthetic.synth_mcmc import truths as TRUTHS_LOG
+    task = _cpu_task_reference if reference_present() else _cpu_task_port
     data = load_datasets()
     rng = np.random.RandomState(1234 + seed)
     procs = procs or os.cpu_count() or 1
     tasks = []
     for i in range(n_evals):
         name = DATASETS[i % len(DATASETS)]
-        tasks.append((O.SYNTH_TRUTHS_LOG[name] + 1e-4 * rng.randn(6), *data[name]))
+        tasks.append((TRUTHS_LOG[name] + 1e-4 * rng.randn(6), *data[name]))
     with get_context("fork").Pool(procs) as pool:
-        pool.map(_cpu_task, tasks[:procs])          # warm the workers (imports)
+        pool.map(task, tasks[:procs])          # warm the workers (imports)
         t0 = time.perf_counter()
-        pool.map(_cpu_task, tasks, chunksize=1)
+        pool.map(task, tasks, chunksize=1)
         dt = time.perf_counter() - t0
     return n_evals / dt, dt, procs
+
+
+def cpu_description():
+    import scipy
+    if reference_present():
+        return f"unmodified reference lnprob/model_lum imported from {REF_ROOT} (scipy {scipy.__version__} odeint)"
+    return (f"oracle port = scipy {scipy.__version__} odeint (LSODA) restatement of the reference path "
+            f"({REF_ROOT} is not on this box)")
 
 
 def run_reference(args):
@@ -112,7 +166,6 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     per_step = 64 * cores          # ~2 s of CPU work per step on this box
-    import scipy
     vals = []
     for s in range(args.warmup + args.steps):
         v, dt, procs = cpu_throughput(per_step, seed=s)
@@ -124,11 +177,10 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean([dt for _, dt in vals]) * 1e3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(workload_config(args), sample=f"{per_step} walkers per step across {cores} processes"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} lnprob evaluations per step, {args.steps} steps, "
-                                   f"multiprocessing.Pool({cores}); oracle = scipy {scipy.__version__} odeint (LSODA) "
-                                   "restatement of the reference path"},
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu_kind(),
+                         "sample": f"{per_step} walker draws of the workload per step ({per_step} lnprob evaluations), "
+                                   f"{args.steps} steps, multiprocessing.Pool({cores}); " + cpu_description()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -200,8 +252,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
-            os.environ["NCCL_DEBUG"] = "NONE"        # NCCL prints its version banner on stdout at both levels; stdout carries one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     data = load_datasets()
@@ -292,10 +342,9 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu:
         n_cpu = args.cpu_evals or 320 * (os.cpu_count() or 1)   # ~10 s of host work
         v, dt, procs = cpu_throughput(n_cpu)
-        import scipy
-        cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+        cpu = {"value": v, "unit": UNIT, "cores": procs, "kind": cpu_kind(),
                "sample": f"{n_cpu} lnprob evaluations of the same walker draws in {dt:.1f} s, multiprocessing.Pool({procs}); "
-                         f"oracle = scipy {scipy.__version__} odeint restatement of the reference path"}
+                         + cpu_description()}
 
     # FP64 roofline of eval_kernel: executed flop (ncu-counted per RHS evaluation, RHS evaluations
     # counted live on the device) over the live-measured launch time, against the live DFMA peak.

@@ -4,7 +4,6 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
-#include <cstdlib>
 #include <numeric>
 #include <vector>
 
@@ -64,10 +63,8 @@ inline Spec make_spec(const mp_model_spec& m) {
   // dominated the global error of plain stepping (measured 5-8x lower median error at equal tolerance);
   // that margin is spent on a 2x looser LOCAL tolerance, 4 rtol on y, calibrated on the 788 golden
   // walkers to give the same max / p99 / median lnprob error as plain stepping at rtol.
-  const char* re = std::getenv("MP_RTOL_Y_SCALE");  // developer knob
-  s.rtol_y = (re ? std::atof(re) : 4.0) * s.rtol;
-  const char* rs = std::getenv("MP_RTOL_STIFF");   // developer knob
-  s.rtol_stiff = rs ? std::atof(rs) : 0.0464 * std::pow(s.rtol, 2.0 / 3.0);
+  s.rtol_y = 4.0 * s.rtol;
+  s.rtol_stiff = 0.0464 * std::pow(s.rtol, 2.0 / 3.0);
   s.max_steps = (m.max_steps > 0) ? m.max_steps : 50000;
   return s;
 }

@@ -417,8 +417,8 @@ struct mp_handle {
   std::map<int, DeviceNodes> curve_nodes;
   // staging for the host-pointer entry points
   double *s_theta = nullptr, *s_out = nullptr, *s_state = nullptr, *s_lnp = nullptr;
-  int *s_status = nullptr, *s_nrhs = nullptr;
-  size_t cap_theta = 0, cap_out = 0, cap_state = 0, cap_w = 0;
+  int *s_status = nullptr, *s_nrhs = nullptr, *s_cstatus = nullptr;
+  size_t cap_theta = 0, cap_out = 0, cap_state = 0, cap_w = 0, cap_cstatus = 0;
   // Two pipeline lanes: each has its own stream and its own stiff-walker queue, so that the
   // host-pointer entry points can overlap the H2D copy of one chunk with the kernel of the previous
   // one.  Device-pointer entry points use lane 0's queue on the caller's stream.
@@ -529,7 +529,7 @@ extern "C" void mp_destroy(mp_handle* h) {
   cudaFree(h->d_lo); cudaFree(h->d_orig);
   for (auto& kv : h->curve_nodes) cudaFree(kv.second.node_t);
   cudaFree(h->s_theta); cudaFree(h->s_out); cudaFree(h->s_state); cudaFree(h->s_lnp);
-  cudaFree(h->s_status); cudaFree(h->s_nrhs);
+  cudaFree(h->s_status); cudaFree(h->s_nrhs); cudaFree(h->s_cstatus);
   for (auto& L : h->lanes) {
     cudaFree(L.queue); cudaFree(L.queue_count); cudaFree(L.resume);
     cudaFree(L.key_in); cudaFree(L.key_out); cudaFree(L.id_in); cudaFree(L.id_out); cudaFree(L.sort_tmp);
@@ -680,7 +680,7 @@ static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lan
     return MP_OK;
   }
   // small ensembles: 32-thread blocks spread the warps over more SMs
-  if (a.W <= 148 * 64 * 4) {
+  if (a.W <= h->sm_count * 64 * 4) {
     eval_kernel<MODE, 32><<<(a.W + 31) / 32, 32, 0, stream>>>(a);
     eval_stiff_kernel<MODE, 32><<<stiff_grid(h, a.W, 32), 32, 0, stream>>>(a);
   } else {
@@ -858,7 +858,10 @@ extern "C" int mp_model_curves(mp_handle* h, const double* pars, int32_t W, int3
   if ((rc = ensure(&h->s_out, &h->cap_out, (size_t)W * 3 * Gs))) return rc;
   if (state && (rc = ensure(&h->s_state, &h->cap_state, (size_t)W * 2 * Gs))) return rc;
   int* d_status = nullptr;
-  if (status) MP_CUDA(cudaMalloc((void**)&d_status, (size_t)W * sizeof(int)));
+  if (status) {
+    if ((rc = ensure(&h->s_cstatus, &h->cap_cstatus, (size_t)W))) return rc;
+    d_status = h->s_cstatus;
+  }
   MP_CUDA(cudaMemcpyAsync(h->s_theta, pars, (size_t)W * ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   rc = mp_model_curves_device(h, h->s_theta, W, ndim, node_stride, h->s_out, state ? h->s_state : nullptr,
                               d_status, h->stream);
@@ -869,7 +872,6 @@ extern "C" int mp_model_curves(mp_handle* h, const double* pars, int32_t W, int3
     cudaError_t e = cudaStreamSynchronize(h->stream);
     if (e != cudaSuccess) rc = fail(MP_ERR_CUDA, std::string("mp_model_curves: ") + cudaGetErrorString(e));
   }
-  if (d_status) cudaFree(d_status);
   return rc;
 }
 
@@ -880,19 +882,21 @@ extern "C" int mp_rhs_batch(const mp_model_spec* spec, const double* y, const do
   if (mp_device_count() <= device || device < 0)
     return fail(MP_ERR_CUDA, "mp_rhs_batch: no such CUDA device (magprop_b200 has no CPU path)");
   MP_CUDA(cudaSetDevice(device));
-  double *d_y = nullptr, *d_t = nullptr, *d_p = nullptr, *d_o = nullptr;
-  MP_CUDA(cudaMalloc((void**)&d_y, (size_t)W * 2 * sizeof(double)));
-  MP_CUDA(cudaMalloc((void**)&d_t, (size_t)W * sizeof(double)));
-  MP_CUDA(cudaMalloc((void**)&d_p, (size_t)W * 5 * sizeof(double)));
-  MP_CUDA(cudaMalloc((void**)&d_o, (size_t)W * 2 * sizeof(double)));
-  MP_CUDA(cudaMemcpy(d_y, y, (size_t)W * 2 * sizeof(double), cudaMemcpyHostToDevice));
-  MP_CUDA(cudaMemcpy(d_t, t, (size_t)W * sizeof(double), cudaMemcpyHostToDevice));
-  MP_CUDA(cudaMemcpy(d_p, pars, (size_t)W * 5 * sizeof(double), cudaMemcpyHostToDevice));
-  rhs_kernel<<<(W + 127) / 128, 128>>>(spec->inertia_factor, spec->mdot_factor, spec->breakup_rhs, spec->dipole_torque, d_y, d_t, d_p,
-                                       knobs[0], knobs[1], knobs[2], knobs[3], W, d_o);
-  MP_CUDA(cudaGetLastError());
-  MP_CUDA(cudaMemcpy(dydt, d_o, (size_t)W * 2 * sizeof(double), cudaMemcpyDeviceToHost));
-  cudaFree(d_y); cudaFree(d_t); cudaFree(d_p); cudaFree(d_o);
+  // one allocation for the four arrays (y[2W] t[W] pars[5W] dydt[2W]), released on every path
+  double* d_all = nullptr;
+  MP_CUDA(cudaMalloc((void**)&d_all, (size_t)W * 10 * sizeof(double)));
+  double *d_y = d_all, *d_t = d_all + (size_t)2 * W, *d_p = d_all + (size_t)3 * W, *d_o = d_all + (size_t)8 * W;
+  cudaError_t e = cudaMemcpy(d_y, y, (size_t)W * 2 * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_t, t, (size_t)W * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_p, pars, (size_t)W * 5 * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    rhs_kernel<<<(W + 127) / 128, 128>>>(spec->inertia_factor, spec->mdot_factor, spec->breakup_rhs, spec->dipole_torque, d_y, d_t, d_p,
+                                         knobs[0], knobs[1], knobs[2], knobs[3], W, d_o);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(dydt, d_o, (size_t)W * 2 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_all);
+  if (e != cudaSuccess) return fail(MP_ERR_CUDA, std::string("mp_rhs_batch: ") + cudaGetErrorString(e));
   return MP_OK;
 }
 
@@ -928,7 +932,7 @@ extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_ln
     MP_CUDA(cudaGetLastError());
     return MP_OK;
   }
-  if (n_active <= 148 * 64 * 4) {
+  if (n_active <= h->sm_count * 64 * 4) {
     stretch_kernel<32><<<(n_active + 31) / 32, 32, 0, (cudaStream_t)stream>>>(s);
     stretch_stiff_kernel<32><<<stiff_grid(h, n_active, 32), 32, 0, (cudaStream_t)stream>>>(s);
   } else {

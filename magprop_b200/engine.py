@@ -98,6 +98,13 @@ class Likelihood:
     def lnprob_async(self, theta: np.ndarray, lnp: np.ndarray, status=None, nrhs=None):
         """Queue lnprob of theta[W, ndim] into the caller's (ideally pinned) float64 buffer ``lnp`` and return
         at once; the result is valid after ``synchronize()``.  Several handles can be in flight together."""
+        for name, arr, dt in (("theta", theta, np.float64), ("lnp", lnp, np.float64), ("status", status, np.int32),
+                              ("nrhs", nrhs, np.int32)):
+            # the pointers go to C as they are: anything but a C-contiguous array of the right type would be read as garbage
+            if arr is not None and not (isinstance(arr, np.ndarray) and arr.dtype == dt and arr.flags.c_contiguous):
+                raise ValueError(f"lnprob_async: {name} must be a C-contiguous {np.dtype(dt).name} ndarray")
+        if theta.ndim != 2 or lnp.shape != (theta.shape[0],):
+            raise ValueError("lnprob_async: theta must be [W, ndim] and lnp [W]")
         W, ndim = theta.shape
         A.check(self._lib.mp_lnprob_batch_async(self._h, A.ptr(theta), W, ndim, A.ptr(lnp),
                                                 A.ptr(status) if status is not None else None,

@@ -1,36 +1,54 @@
-"""Drop-in for the reference's ``magnetar/fit_stats.py`` (``redchisq``, ``aicc``).
+"""Goodness-of-fit numbers of a finished fit: the interface of the reference's
+``magnetar/fit_stats.py`` (``redchisq`` :6-33, ``aicc`` :36-62) on top of ONE weighted
+sum of squared residuals.
 
-Two scalar reductions over a finished fit; they are
-not in the sampler loop, so they stay NumPy on the host exactly as the reference
-has them -- the model values they consume come from the CUDA path."""
+Both statistics are functions of ``chi2 = sum(((ydata - ymod)/sd)^2)``:
+
+    redchisq = chi2 / (N - 1 - deg)                (chi2 itself when ``deg`` is None)
+    aicc     = -chi2 + 2k + 2k(k+1)/(N - k - 1)
+
+so the arithmetic lives in ``_chi2`` and the two public functions only dress it.  For a
+fit held on the GPU the same ``chi2`` comes out of the likelihood kernel
+(``lnlike = -chi2/2``, ``Likelihood.lnprob`` without a prior): ``from_lnlike`` turns that
+number into both statistics without touching the data again.
+"""
 import numpy as np
 
 
-def redchisq(ydata, ymod, deg=None, sd=None):
-    """fit_stats.py:6-33: chi-square, divided by ``ydata.size - 1 - deg`` when ``deg`` is given."""
-    ydata, ymod = np.asarray(ydata), np.asarray(ymod)
+def _chi2(ydata, ymod, sd=None) -> float:
+    """Sum of squared residuals, weighted by ``sd`` when given (NumPy's pairwise ``np.sum``,
+    as the reference uses, so the value is the reference's to the last bit)."""
+    resid = np.asarray(ydata, dtype=np.float64) - np.asarray(ymod, dtype=np.float64)
     if sd is not None:
-        chisq = np.sum(((ydata - ymod) / np.asarray(sd)) ** 2.0)
-    else:
-        chisq = np.sum((ydata - ymod) ** 2.0)
-    if deg is not None:
-        nu = ydata.size - 1.0 - deg
-        return chisq / nu
-    return chisq
+        resid = resid / np.asarray(sd, dtype=np.float64)
+    return np.sum(resid ** 2.0)
+
+
+def redchisq(ydata, ymod, deg=None, sd=None):
+    """Chi-square of ``ymod`` against ``ydata``; divided by the degrees of freedom
+    ``ydata.size - 1 - deg`` when the number of fitted parameters ``deg`` is given."""
+    chi2 = _chi2(ydata, ymod, sd)
+    if deg is None:
+        return chi2
+    return chi2 / (np.size(ydata) - 1.0 - deg)
 
 
 def aicc(ydata, ymod, yerr, Npars):
-    """fit_stats.py:36-62: corrected Akaike information criterion; ``ValueError`` on a length mismatch."""
-    ydata, ymod, yerr = np.asarray(ydata), np.asarray(ymod), np.asarray(yerr)
-    cond1 = ydata.size == ymod.size
-    cond2 = ydata.size == yerr.size
-    cond3 = ymod.size == yerr.size
-    if (not cond1) or (not cond2) or (not cond3):
-        print("ydata.size == ymod.size:", cond1)
-        print("ydata.size == yerr.size:", cond2)
-        print("ymod.size == yerr.size:", cond3)
+    """Corrected Akaike information criterion.  The three arrays must have one length;
+    the reference reports which pair disagrees before raising, and so does this."""
+    sizes = {"ydata": np.size(ydata), "ymod": np.size(ymod), "yerr": np.size(yerr)}
+    if len(set(sizes.values())) != 1:
+        for a, b in (("ydata", "ymod"), ("ydata", "yerr"), ("ymod", "yerr")):
+            print(f"{a}.size == {b}.size:", sizes[a] == sizes[b])
         raise ValueError("ydata, ymod and yerr should all be the same length")
-    a = -1.0 * np.sum(((ydata - ymod) / yerr) ** 2.0)
-    b = 2.0 * Npars
-    c = ((2.0 * Npars) * (Npars + 1.0)) / (ydata.size - Npars - 1.0)
-    return a + b + c
+    return _aicc_from_chi2(_chi2(ydata, ymod, yerr), sizes["ydata"], Npars)
+
+
+def _aicc_from_chi2(chi2, n, k):
+    return -1.0 * chi2 + 2.0 * k + ((2.0 * k) * (k + 1.0)) / (n - k - 1.0)
+
+
+def from_lnlike(lnlike, n_data, n_pars):
+    """(reduced chi-square, AICc) from the likelihood kernel's ``lnlike = -chi2/2``."""
+    chi2 = -2.0 * float(lnlike)
+    return chi2 / (n_data - 1.0 - n_pars), _aicc_from_chi2(chi2, n_data, n_pars)
