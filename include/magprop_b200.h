@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define MP_ABI_VERSION 1
+#define MP_ABI_VERSION 2
 #define MP_MAX_NDIM 9
 
 /* ---- return codes ------------------------------------------------------- */
@@ -173,6 +173,75 @@ int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_lnp, int32_t 
                          const int32_t* d_complement, int32_t n_complement,
                          double a, uint64_t seed, uint64_t step, int32_t* d_accepted,
                          int32_t* d_n_rhs, void* stream);
+
+/* ---- device-resident ensemble (emcee's RedBlueMove, synth_mcmc.py:180-185) -------------------
+ * The ensemble a sampler keeps: positions and log-probabilities on the device, replicated on every
+ * rank of a multi-GPU run.  One MCMC step is two half-steps (split = 0, 1).  In half-step `split` the
+ * walkers of half `split` are moved against the other half -- which includes the updates the first
+ * half-step of the same step made, as in emcee.
+ *
+ * Which walkers form the halves: position g of the ensemble order holds walker P(g); half 0 is
+ * g in [0, n/2), half 1 is g in [n/2, n).  randomize_split = 1 makes P a pseudo-random permutation
+ * keyed by (seed, step) -- emcee's `inds = arange(n) % 2; random.shuffle(inds)` re-drawn every step --
+ * computed on the fly inside the kernel (a cycle-walking Feistel network), so every rank of a sharded run
+ * derives the same split without communication.  randomize_split = 0: P = identity (fixed halves).
+ *
+ * Sharding: rank r of `world` moves positions [r*m, (r+1)*m) of the active half, m = n/2/world.  The rows
+ * it moves must reach the other ranks' replicas before the next half-step.  Two ways:
+ *   peer stores   peer_coords/peer_lnp hold the other ranks' replicas mapped into this process (mp_peer_open,
+ *                 NVLink): the kernel's epilogue stores every accepted row straight into each of them; the
+ *                 caller then runs mp_peer_barrier.  No collective is launched.
+ *   packed rows   pack_out [m][ndim+1] receives every moved walker's (row, lnp) in position order; the
+ *                 caller all-gathers the ranks' packs and scatters them with mp_ensemble_unpack (one
+ *                 collective per half-step; this is also what the gloo CPU tests drive).
+ *
+ * status[n] (may be NULL) receives the MP_WALKER_* bits of each walker's latest proposal.  bad_rows /
+ * bad_count (may be NULL) log the proposals whose likelihood was not finite -- the rows the reference
+ * appends to {GRB}_bad.csv (mcmc_eqns.py:72-79); at most bad_capacity rows are kept, bad_count keeps
+ * counting.                                                                                        */
+#define MP_MAX_PEERS 15
+typedef struct mp_ensemble {
+  double* coords;            /* [nwalkers][ndim] */
+  double* lnp;               /* [nwalkers]        */
+  int32_t nwalkers, ndim;
+  double a;                  /* stretch scale (emcee default 2.0) */
+  uint64_t seed;
+  int32_t randomize_split;
+  int32_t rank, world;
+  int32_t* accepted;         /* [nwalkers] acceptance counters, or NULL */
+  int32_t* status;           /* [nwalkers] or NULL */
+  int32_t* n_rhs;            /* [nwalkers] or NULL */
+  int32_t n_peers;           /* entries used below (0: no peer stores) */
+  double* peer_coords[MP_MAX_PEERS];
+  double* peer_lnp[MP_MAX_PEERS];
+  double* pack_out;          /* [nwalkers/2/world][ndim+1] or NULL */
+  double* bad_rows;          /* [bad_capacity][ndim] or NULL */
+  int32_t* bad_count;        /* [1] or NULL */
+  int32_t bad_capacity;
+} mp_ensemble;
+
+/* One half-step for this rank's share of half `split` at MCMC step `step`: proposal, lnprob, accept, in one
+ * fused launch (plus the stiff-bucket launch).  Counter-based RNG (Philox4x32-10) keyed by seed with counter
+ * (2*step + split, walker): any rank reproduces any walker's draws.  Enqueues on `stream`.             */
+int mp_ensemble_half_step(mp_handle* h, const mp_ensemble* ens, uint64_t step, int32_t split, void* stream);
+/* Scatter all-gathered packs ([nwalkers/2][ndim+1], position order) of half `split` into coords / lnp.  */
+int mp_ensemble_unpack(const mp_ensemble* ens, uint64_t step, int32_t split, const double* d_packed, void* stream);
+/* The ensemble order itself: d_order[g] = P(g) for g in [0, nwalkers) (tests, host-side bookkeeping).   */
+int mp_ensemble_order(int32_t nwalkers, uint64_t seed, uint64_t step, int32_t randomize_split,
+                      int32_t* d_order, void* stream);
+
+/* Peer-mappable device memory for the replicas (CUDA IPC; one process per GPU on one node).
+ * mp_peer_alloc: cudaMalloc + export a 64-byte handle other processes pass to mp_peer_open, which maps the
+ * block into the caller's address space on `device` (NVLink peer access).  mp_peer_barrier: every rank calls
+ * it with the same `epoch` after a half-step; it raises flag[rank] = epoch in every peer's flag array and
+ * waits until every peer has raised its own in `my_flags` -- after which all peer stores of the half-step
+ * are visible.  A peer that does not arrive within ~10 s sets *d_error = 1 instead of hanging.          */
+int mp_peer_alloc(int32_t device, uint64_t bytes, void** d_ptr, unsigned char handle[64]);
+int mp_peer_open(int32_t device, const unsigned char handle[64], void** d_ptr);
+int mp_peer_close(int32_t device, void* d_ptr);
+int mp_peer_free(int32_t device, void* d_ptr);
+int mp_peer_barrier(int32_t device, uint64_t* d_my_flags, uint64_t* const* peer_flags, int32_t rank,
+                    int32_t world, uint64_t epoch, int32_t* d_error, void* stream);
 
 /* Diagnostic: how many walkers of the most recent launch on this handle were bucketed as stiff
  * and re-run by the implicit (Radau IIA) launch.  Synchronises the device.               */

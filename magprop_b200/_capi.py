@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 MP_MAX_NDIM = 9
-MP_ABI_VERSION = 1
+MP_ABI_VERSION = 2
+MP_MAX_PEERS = 15
 
 MP_OK, MP_ERR_BAD_ARG, MP_ERR_DATA_RANGE, MP_ERR_CUDA, MP_ERR_BAD_GRID, MP_ERR_NO_DATA = range(6)
 
@@ -40,6 +41,18 @@ class PriorSpec(C.Structure):
     """mp_prior_spec."""
     _fields_ = [("ndim", C.c_int32), ("enabled", C.c_int32),
                 ("lower", C.c_double * MP_MAX_NDIM), ("upper", C.c_double * MP_MAX_NDIM)]
+
+
+class Ensemble(C.Structure):
+    """mp_ensemble (include/magprop_b200.h): a device-resident ensemble and how this rank moves it."""
+    _fields_ = [("coords", C.c_void_p), ("lnp", C.c_void_p), ("nwalkers", C.c_int32), ("ndim", C.c_int32),
+                ("a", C.c_double), ("seed", C.c_uint64), ("randomize_split", C.c_int32),
+                ("rank", C.c_int32), ("world", C.c_int32),
+                ("accepted", C.c_void_p), ("status", C.c_void_p), ("n_rhs", C.c_void_p),
+                ("n_peers", C.c_int32),
+                ("peer_coords", C.c_void_p * MP_MAX_PEERS), ("peer_lnp", C.c_void_p * MP_MAX_PEERS),
+                ("pack_out", C.c_void_p), ("bad_rows", C.c_void_p), ("bad_count", C.c_void_p),
+                ("bad_capacity", C.c_int32)]
 
 
 def script_model_spec(n=10.0, alpha=0.1, cs7=1.0, k=0.9, dipeff=1.0, propeff=1.0, f_beam=1.0,
@@ -121,6 +134,14 @@ def declare(lib):
     lib.mp_rhs_batch.argtypes = [C.POINTER(ModelSpec), vp, vp, vp, vp, C.c_int32, vp, C.c_int32]
     lib.mp_stretch_half_step.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32,
                                          C.c_double, C.c_uint64, C.c_uint64, vp, vp, vp]
+    lib.mp_ensemble_half_step.argtypes = [vp, C.POINTER(Ensemble), C.c_uint64, C.c_int32, vp]
+    lib.mp_ensemble_unpack.argtypes = [C.POINTER(Ensemble), C.c_uint64, C.c_int32, vp, vp]
+    lib.mp_ensemble_order.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, vp, vp]
+    lib.mp_peer_alloc.argtypes = [C.c_int32, C.c_uint64, C.POINTER(vp), C.c_char_p]
+    lib.mp_peer_open.argtypes = [C.c_int32, C.c_char_p, C.POINTER(vp)]
+    lib.mp_peer_close.argtypes = [C.c_int32, vp]
+    lib.mp_peer_free.argtypes = [C.c_int32, vp]
+    lib.mp_peer_barrier.argtypes = [C.c_int32, vp, C.POINTER(vp), C.c_int32, C.c_int32, C.c_uint64, vp, vp]
     lib.mp_fp64_peak_tflops.argtypes = [C.c_int32, _dp]
     lib.mp_last_stiff_count.argtypes = [vp, _ip]
     return lib
@@ -129,7 +150,9 @@ def declare(lib):
 EXPORTS = ["mp_abi_version", "mp_device_count", "mp_last_error", "mp_create", "mp_destroy",
            "mp_set_prior", "mp_set_bucketing", "mp_lnprob_batch", "mp_lnprob_batch_async", "mp_synchronize", "mp_lnprob_batch_device", "mp_model_at_data",
            "mp_curve_nodes", "mp_model_curves", "mp_model_curves_device", "mp_rhs_batch",
-           "mp_stretch_half_step", "mp_fp64_peak_tflops", "mp_last_stiff_count"]
+           "mp_stretch_half_step", "mp_fp64_peak_tflops", "mp_last_stiff_count",
+           "mp_ensemble_half_step", "mp_ensemble_unpack", "mp_ensemble_order",
+           "mp_peer_alloc", "mp_peer_open", "mp_peer_close", "mp_peer_free", "mp_peer_barrier"]
 
 
 def load():

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "magprop_host.hpp"
+#include "magprop_rng.cuh"
 
 namespace mp {
 
@@ -199,54 +200,44 @@ __global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) eval_s
                               (MODE != kModeCurves && a.resume && have) ? a.resume + (size_t)i * kResumeLen : nullptr);
 }
 
-// ---- counter-based RNG: Philox4x32-10 (Salmon et al. 2011) -------------------
-struct Philox {
-  uint32_t c[4];
-};
-__host__ __device__ inline Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                uint32_t k0, uint32_t k1) {
-  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-  for (int r = 0; r < 10; ++r) {
-    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
-    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-    const uint32_t n1 = (uint32_t)p1;
-    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-    const uint32_t n3 = (uint32_t)p0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += W0; k1 += W1;
-  }
-  Philox o;
-  o.c[0] = c0; o.c[1] = c1; o.c[2] = c2; o.c[3] = c3;
-  return o;
-}
-// 53-bit uniform in (0,1): never 0 so log() is finite
-__host__ __device__ inline double u01(uint32_t hi, uint32_t lo) {
-  const uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;
-  return ((double)v + 0.5) * (1.0 / 9007199254740992.0);
-}
-
 struct StretchArgs {
   KernelArgs k;          // k.theta unused; k.lnp unused
   double* coords;        // [nwalkers][ndim], updated in place
   double* lnp;           // [nwalkers]
-  const int* active;     // [n_active] walkers to move (disjoint from complement)
+  // who moves against whom: explicit index lists (mp_stretch_half_step) ...
+  const int* active;     // [n_active] walkers to move (disjoint from complement), or null
   const int* complement; // [n_complement]
+  // ... or positions of the ensemble order (mp_ensemble_half_step): mover i is walker P(pos0 + i), its
+  // partner is drawn from P(cpos0 + [0, n_complement))
+  SplitPerm perm;
+  int pos0, cpos0;
   int n_active, n_complement;
   double a;
-  uint64_t seed, step;
+  uint64_t seed, step;   // step: the half-step counter (RNG counter word)
   int* accepted;         // [nwalkers] counters (may be null)
+  int* status;           // [nwalkers] MP_WALKER_* bits of the latest proposal (may be null)
+  // replicas of (coords, lnp) on the other ranks, peer-mapped over NVLink: accepted rows are stored there too
+  int n_peers;
+  double* peer_coords[MP_MAX_PEERS];
+  double* peer_lnp[MP_MAX_PEERS];
+  double* pack_out;      // [n_active][ndim+1]: every mover's (row, lnp) after the move, or null
+  double* bad_rows;      // proposals whose likelihood was not finite ({GRB}_bad.csv, mcmc_eqns.py:72-79)
+  int* bad_count;
+  int bad_capacity;
 };
 
 // One emcee StretchMove half-step (Goodman & Weare 2010; emcee RedBlueMove):
 //   z = ((a-1) u + 1)^2 / a ; q = c - (c - s) z ; accept iff (ndim-1) ln z + lp(q) - lp(s) > ln u'
 // fused with the likelihood so a half-step is one launch (plus the stiff-bucket launch, which
-// finds an empty queue for ensembles near the synthetic truths).  Returns true when deferred.
+// finds an empty queue for ensembles near the synthetic truths).  `i` is the mover's index in this
+// launch.  Returns true when deferred.
 template <int BLOCK, bool STIFF>
-__device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int me, double* s_buf, ResumeSink* sink = nullptr,
+__device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int i, double* s_buf, ResumeSink* sink = nullptr,
                                             const double* rec_in = nullptr) {
   const KernelArgs& a = s.k;
   const int ndim = a.ndim;
-  // counter = (step, walker); two Philox blocks give u_z, u_partner, u_accept
+  const int me = s.active ? s.active[i] : (int)perm_at(s.perm, (uint32_t)(s.pos0 + i));
+  // counter = (half-step, walker); two Philox blocks give u_z, u_partner, u_accept
   const Philox r0 = philox4x32_10((uint32_t)s.step, (uint32_t)(s.step >> 32), (uint32_t)me, 0u,
                                   (uint32_t)s.seed, (uint32_t)(s.seed >> 32));
   const Philox r1 = philox4x32_10((uint32_t)s.step, (uint32_t)(s.step >> 32), (uint32_t)me, 1u,
@@ -258,7 +249,7 @@ __device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int
   const double z = __ddiv_rn(__dmul_rn(zr, zr), s.a);
   int pj = (int)(up * s.n_complement);
   if (pj >= s.n_complement) pj = s.n_complement - 1;
-  const int partner = s.complement[pj];
+  const int partner = s.complement ? s.complement[pj] : (int)perm_at(s.perm, (uint32_t)(s.cpos0 + pj));
   double q[MP_MAX_NDIM];
   for (int d = 0; d < ndim; ++d) {
     const double c = s.coords[(size_t)partner * ndim + d];
@@ -268,6 +259,7 @@ __device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int
   int st = kWalkerOk, nr = 0;
   double lp_new = -INFINITY;
   const bool live = have && (!a.prior_enabled || prior_accepts(q, ndim, a.lower, a.upper));
+  if (have && !live) st = kWalkerPriorReject;
   {
     double pars[6], dipeff, propeff, f_beam;
     unpack_theta(a.sp, q, ndim, pars, dipeff, propeff, f_beam);
@@ -278,17 +270,41 @@ __device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int
     if (!STIFF && (st & kWalkerDeferred)) return true;
     if (live) {
       double ll = -0.5 * chi2;
-      if ((st & kWalkerIntegratorFail) || !isfinite(ll)) ll = -INFINITY;
+      if (st & kWalkerIntegratorFail) {
+        ll = -INFINITY;
+      } else if (!isfinite(ll)) {
+        st |= kWalkerNonfiniteLnlike;
+        ll = -INFINITY;
+      }
       lp_new = ll;
     }
   }
   if (!have) return false;
   const double lp_old = s.lnp[me];
   const double lnpdiff = __dadd_rn(__dadd_rn(__dmul_rn(ndim - 1.0, log(z)), lp_new), -lp_old);
-  if (lnpdiff > log(ua)) {
+  const bool accept = lnpdiff > log(ua);
+  if (accept) {
     for (int d = 0; d < ndim; ++d) s.coords[(size_t)me * ndim + d] = q[d];
     s.lnp[me] = lp_new;
+    // the same row into every other rank's replica (NVLink peer stores; the caller's mp_peer_barrier
+    // makes them visible before the next half-step reads them)
+    for (int p = 0; p < s.n_peers; ++p) {
+      double* pc = s.peer_coords[p] + (size_t)me * ndim;
+      for (int d = 0; d < ndim; ++d) pc[d] = q[d];
+      s.peer_lnp[p][me] = lp_new;
+    }
     if (s.accepted) s.accepted[me] += 1;
+  }
+  if (s.pack_out) {
+    double* row = s.pack_out + (size_t)i * (ndim + 1);
+    for (int d = 0; d < ndim; ++d) row[d] = accept ? q[d] : s.coords[(size_t)me * ndim + d];
+    row[ndim] = accept ? lp_new : lp_old;
+  }
+  if (s.status) s.status[me] = st;
+  if (s.bad_count && (st & (kWalkerIntegratorFail | kWalkerNonfiniteLnlike))) {
+    const int slot = atomicAdd(s.bad_count, 1);
+    if (slot < s.bad_capacity)
+      for (int d = 0; d < ndim; ++d) s.bad_rows[(size_t)slot * ndim + d] = q[d];
   }
   if (a.n_rhs) a.n_rhs[me] = nr;
   return false;
@@ -300,10 +316,9 @@ stretch_kernel(const __grid_constant__ StretchArgs s) {
   __shared__ double s_buf[kNB * BLOCK];
   const int i = blockIdx.x * BLOCK + threadIdx.x;
   const bool have = i < s.n_active;
-  const int me = have ? s.active[i] : s.active[0];
   ResumeSink sink{s.k.resume ? s.k.queue_count : nullptr, s.k.resume, -1};
-  if (stretch_one<BLOCK, false>(s, have, me, s_buf, &sink))
-    s.k.queue[sink.count ? sink.slot : atomicAdd(s.k.queue_count, 1)] = me;
+  if (stretch_one<BLOCK, false>(s, have, have ? i : 0, s_buf, &sink))
+    s.k.queue[sink.count ? sink.slot : atomicAdd(s.k.queue_count, 1)] = i;
 }
 
 template <int BLOCK>
@@ -313,8 +328,52 @@ __global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) stretc
   const int i = blockIdx.x * BLOCK + threadIdx.x;
   if (blockIdx.x * BLOCK >= n) return;
   const bool have = i < n;
-  stretch_one<BLOCK, true>(s, have, have ? s.k.queue[i] : s.active[0], s_buf, nullptr,
+  stretch_one<BLOCK, true>(s, have, have ? s.k.queue[i] : 0, s_buf, nullptr,
                            (s.k.resume && have) ? s.k.resume + (size_t)i * kResumeLen : nullptr);
+}
+
+// Scatter of all-gathered packs (the collective exchange): packed row i of the half -> walker P(pos0 + i).
+__global__ void unpack_kernel(SplitPerm perm, int pos0, int n, int ndim, const double* __restrict__ packed,
+                              double* __restrict__ coords, double* __restrict__ lnp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t w = perm_at(perm, (uint32_t)(pos0 + i));
+  const double* row = packed + (size_t)i * (ndim + 1);
+  for (int d = 0; d < ndim; ++d) coords[w * ndim + d] = row[d];
+  lnp[w] = row[ndim];
+}
+
+__global__ void order_kernel(SplitPerm perm, int n, int* __restrict__ order) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n) order[g] = (int)perm_at(perm, (uint32_t)g);
+}
+
+// ---- cross-GPU flag barrier over peer-mapped memory ---------------------------------------------
+// Thread p of the one block: raise flag[rank] = epoch in peer p's array (a system-scope release, after the
+// preceding kernel's peer stores -- stream order plus the fence make them visible first), then spin on
+// this rank's own array until peer p has raised its flag (system-scope acquire).  The spin is on LOCAL
+// memory; the only NVLink traffic is one 8-byte store per peer.
+struct PeerFlags {
+  uint64_t* p[MP_MAX_PEERS + 1];
+};
+__global__ void peer_barrier_kernel(uint64_t* my_flags, PeerFlags pf, int rank, int world, uint64_t epoch, int* error) {
+  const int p = threadIdx.x;
+  if (p >= world || p == rank) return;
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pf.p[p] + rank), "l"(epoch) : "memory");
+  unsigned long long t0, t1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(my_flags + p) : "memory");
+    if (v >= epoch) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 10000000000ull) {   // 10 s: a peer died -- report instead of hanging the GPU
+      if (error) *error = 1;
+      break;
+    }
+    __nanosleep(200);
+  }
 }
 
 // ---- the coupled right-hand side, as ODEs()/odes() return it -----------------------
@@ -435,9 +494,15 @@ struct mp_handle {
     void* sort_tmp = nullptr;
     size_t cap_sort = 0, cap_tmp = 0;
   } lanes[2];
+  // Device-pointer entry points run on the caller's stream.  Each stream gets its own queue set, so calls
+  // on one handle from different streams (several ensembles on one dataset, a device call next to an
+  // mp_lnprob_batch_async in flight) never share a stiff queue; calls on ONE stream are ordered by the stream.
+  std::map<cudaStream_t, Lane> user_lanes;
+  std::mutex user_lanes_mu;
   int bucketing = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;   // == lanes[0].stream
+  Lane* last_lane = nullptr;       // queue set of the most recent device-pointer launch (mp_last_stiff_count)
 };
 
 template <typename T>
@@ -530,11 +595,13 @@ extern "C" void mp_destroy(mp_handle* h) {
   for (auto& kv : h->curve_nodes) cudaFree(kv.second.node_t);
   cudaFree(h->s_theta); cudaFree(h->s_out); cudaFree(h->s_state); cudaFree(h->s_lnp);
   cudaFree(h->s_status); cudaFree(h->s_nrhs); cudaFree(h->s_cstatus);
-  for (auto& L : h->lanes) {
+  auto free_lane = [](mp_handle::Lane& L) {
     cudaFree(L.queue); cudaFree(L.queue_count); cudaFree(L.resume);
     cudaFree(L.key_in); cudaFree(L.key_out); cudaFree(L.id_in); cudaFree(L.id_out); cudaFree(L.sort_tmp);
     if (L.stream) cudaStreamDestroy(L.stream);
-  }
+  };
+  for (auto& L : h->lanes) free_lane(L);
+  for (auto& kv : h->user_lanes) free_lane(kv.second);     // (their .stream is null: the streams are the callers')
   delete h;
 }
 
@@ -580,9 +647,29 @@ static int fill_args(mp_handle* h, KernelArgs& a, const DeviceNodes& nodes, bool
   return MP_OK;
 }
 
-static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream, int lane = 0) {
-  mp_handle::Lane& L = h->lanes[lane];
-  int rc = ensure(&L.queue, &L.cap_queue, (size_t)W);
+// lane >= 0: one of the handle's own pipeline lanes; lane < 0: the queue set of the caller's stream
+static int lane_for(mp_handle* h, cudaStream_t stream, int lane, mp_handle::Lane** out) {
+  if (lane >= 0) {
+    *out = &h->lanes[lane];
+    return MP_OK;
+  }
+  std::lock_guard<std::mutex> g(h->user_lanes_mu);
+  mp_handle::Lane& L = h->user_lanes[stream];
+  if (!L.queue_count) {
+    MP_CUDA(cudaMalloc((void**)&L.queue_count, sizeof(int)));
+    MP_CUDA(cudaMemsetAsync(L.queue_count, 0, sizeof(int), stream));
+  }
+  h->last_lane = &L;
+  *out = &L;
+  return MP_OK;
+}
+
+static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream, int lane = -1) {
+  mp_handle::Lane* Lp = nullptr;
+  int rc = lane_for(h, stream, lane, &Lp);
+  if (rc) return rc;
+  mp_handle::Lane& L = *Lp;
+  rc = ensure(&L.queue, &L.cap_queue, (size_t)W);
   if (rc) return rc;
   if ((rc = ensure(&L.resume, &L.cap_resume, (size_t)W * kResumeLen))) return rc;
   a.queue = L.queue;
@@ -619,7 +706,10 @@ __global__ void bucket_key_kernel(const double* __restrict__ theta, int W, int n
 }
 
 static int bucket_walkers(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane) {
-  mp_handle::Lane& L = h->lanes[lane];
+  mp_handle::Lane* Lp = nullptr;
+  int rc0 = lane_for(h, stream, lane, &Lp);
+  if (rc0) return rc0;
+  mp_handle::Lane& L = *Lp;
   const size_t W = (size_t)a.W;
   if (W > L.cap_sort) {
     cudaFree(L.key_in); cudaFree(L.key_out); cudaFree(L.id_in); cudaFree(L.id_out);
@@ -652,7 +742,7 @@ __global__ void queue_all_kernel(int* queue, int* count, int W, const int* ids =
 }
 
 template <int MODE>
-static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane = 0) {
+static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane = -1) {
   if (a.W == 0) return MP_OK;
   int rc = prepare_queue(h, a, a.W, stream, lane);
   if (rc) return rc;
@@ -795,7 +885,7 @@ extern "C" int mp_model_at_data(mp_handle* h, const double* pars, int32_t W, int
   a.theta = h->s_theta;
   a.out = h->s_out;
   a.status = h->s_status;
-  if ((rc = launch_eval<kModeModelAtData>(h, a, h->stream))) return rc;
+  if ((rc = launch_eval<kModeModelAtData>(h, a, h->stream, 0))) return rc;
   MP_CUDA(cudaMemcpyAsync(out, h->s_out, (size_t)W * h->D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (status) MP_CUDA(cudaMemcpyAsync(status, h->s_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   MP_CUDA(cudaStreamSynchronize(h->stream));
@@ -900,6 +990,29 @@ extern "C" int mp_rhs_batch(const mp_model_spec* spec, const double* y, const do
   return MP_OK;
 }
 
+static int launch_stretch(mp_handle* h, StretchArgs& s, cudaStream_t stream) {
+  const int n_active = s.n_active;
+  if (n_active == 0) return MP_OK;
+  int rc;
+  if ((rc = prepare_queue(h, s.k, n_active, stream))) return rc;
+  if (s.k.sp.bucciantini) {
+    s.k.resume = nullptr;
+    queue_all_kernel<<<(n_active + 255) / 256, 256, 0, stream>>>(s.k.queue, s.k.queue_count, n_active);
+    stretch_stiff_kernel<64><<<(n_active + 63) / 64, 64, 0, stream>>>(s);
+    MP_CUDA(cudaGetLastError());
+    return MP_OK;
+  }
+  if (n_active <= h->sm_count * 64 * 4) {
+    stretch_kernel<32><<<(n_active + 31) / 32, 32, 0, stream>>>(s);
+    stretch_stiff_kernel<32><<<stiff_grid(h, n_active, 32), 32, 0, stream>>>(s);
+  } else {
+    stretch_kernel<64><<<(n_active + 63) / 64, 64, 0, stream>>>(s);
+    stretch_stiff_kernel<64><<<stiff_grid(h, n_active, 64), 64, 0, stream>>>(s);
+  }
+  MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
 extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_lnp, int32_t nwalkers,
                                     int32_t ndim, const int32_t* d_active, int32_t n_active,
                                     const int32_t* d_complement, int32_t n_complement, double a,
@@ -910,6 +1023,7 @@ extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_ln
     return fail(MP_ERR_BAD_ARG, "mp_stretch_half_step: null pointer or empty set");
   MP_CUDA(cudaSetDevice(h->device));
   StretchArgs s;
+  std::memset(&s, 0, sizeof(s));
   int rc = fill_args(h, s.k, h->data_nodes, true, ndim, n_active, true);
   if (rc) return rc;
   s.k.n_rhs = d_n_rhs;
@@ -923,22 +1037,133 @@ extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_ln
   s.seed = seed;
   s.step = step;
   s.accepted = d_accepted;
-  if (n_active == 0) return MP_OK;
-  if ((rc = prepare_queue(h, s.k, n_active, (cudaStream_t)stream))) return rc;
-  if (s.k.sp.bucciantini) {
-    s.k.resume = nullptr;
-    queue_all_kernel<<<(n_active + 255) / 256, 256, 0, (cudaStream_t)stream>>>(s.k.queue, s.k.queue_count, n_active, d_active);
-    stretch_stiff_kernel<64><<<(n_active + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s);
-    MP_CUDA(cudaGetLastError());
-    return MP_OK;
+  return launch_stretch(h, s, (cudaStream_t)stream);
+}
+
+static int check_ensemble(const mp_ensemble* e, const char* who) {
+  if (!e || !e->coords || !e->lnp) return fail(MP_ERR_BAD_ARG, std::string(who) + ": null ensemble / coords / lnp");
+  if (e->nwalkers < 2 || (e->nwalkers & 1)) return fail(MP_ERR_BAD_ARG, std::string(who) + ": nwalkers must be even");
+  if (e->world < 1 || e->rank < 0 || e->rank >= e->world || (e->nwalkers / 2) % e->world)
+    return fail(MP_ERR_BAD_ARG, std::string(who) + ": half-ensemble does not split evenly over the ranks");
+  if (e->n_peers < 0 || e->n_peers > MP_MAX_PEERS) return fail(MP_ERR_BAD_ARG, std::string(who) + ": bad n_peers");
+  return MP_OK;
+}
+
+extern "C" int mp_ensemble_half_step(mp_handle* h, const mp_ensemble* e, uint64_t step, int32_t split, void* stream) {
+  if (!h) return fail(MP_ERR_BAD_ARG, "mp_ensemble_half_step: null handle");
+  int rc = check_ensemble(e, "mp_ensemble_half_step");
+  if (rc) return rc;
+  if (split != 0 && split != 1) return fail(MP_ERR_BAD_ARG, "mp_ensemble_half_step: split must be 0 or 1");
+  MP_CUDA(cudaSetDevice(h->device));
+  const int half = e->nwalkers / 2, m = half / e->world;
+  StretchArgs s;
+  std::memset(&s, 0, sizeof(s));
+  if ((rc = fill_args(h, s.k, h->data_nodes, true, e->ndim, m, true))) return rc;
+  s.k.n_rhs = e->n_rhs;
+  s.coords = e->coords;
+  s.lnp = e->lnp;
+  s.perm = make_split_perm(e->nwalkers, e->seed, step, e->randomize_split);
+  s.pos0 = split * half + e->rank * m;
+  s.cpos0 = (1 - split) * half;
+  s.n_active = m;
+  s.n_complement = half;
+  s.a = e->a;
+  s.seed = e->seed;
+  s.step = 2 * step + (uint64_t)split;
+  s.accepted = e->accepted;
+  s.status = e->status;
+  s.n_peers = e->n_peers;
+  for (int p = 0; p < e->n_peers; ++p) {
+    if (!e->peer_coords[p] || !e->peer_lnp[p]) return fail(MP_ERR_BAD_ARG, "mp_ensemble_half_step: null peer replica");
+    s.peer_coords[p] = e->peer_coords[p];
+    s.peer_lnp[p] = e->peer_lnp[p];
   }
-  if (n_active <= h->sm_count * 64 * 4) {
-    stretch_kernel<32><<<(n_active + 31) / 32, 32, 0, (cudaStream_t)stream>>>(s);
-    stretch_stiff_kernel<32><<<stiff_grid(h, n_active, 32), 32, 0, (cudaStream_t)stream>>>(s);
-  } else {
-    stretch_kernel<64><<<(n_active + 63) / 64, 64, 0, (cudaStream_t)stream>>>(s);
-    stretch_stiff_kernel<64><<<stiff_grid(h, n_active, 64), 64, 0, (cudaStream_t)stream>>>(s);
+  s.pack_out = e->pack_out;
+  if (e->bad_rows && e->bad_count && e->bad_capacity > 0) {
+    s.bad_rows = e->bad_rows;
+    s.bad_count = e->bad_count;
+    s.bad_capacity = e->bad_capacity;
   }
+  return launch_stretch(h, s, (cudaStream_t)stream);
+}
+
+extern "C" int mp_ensemble_unpack(const mp_ensemble* e, uint64_t step, int32_t split, const double* d_packed, void* stream) {
+  int rc = check_ensemble(e, "mp_ensemble_unpack");
+  if (rc) return rc;
+  if (!d_packed || (split != 0 && split != 1)) return fail(MP_ERR_BAD_ARG, "mp_ensemble_unpack: bad argument");
+  const int half = e->nwalkers / 2;
+  const SplitPerm perm = make_split_perm(e->nwalkers, e->seed, step, e->randomize_split);
+  unpack_kernel<<<(half + 255) / 256, 256, 0, (cudaStream_t)stream>>>(perm, split * half, half, e->ndim, d_packed, e->coords, e->lnp);
+  MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
+extern "C" int mp_ensemble_order(int32_t nwalkers, uint64_t seed, uint64_t step, int32_t randomize_split,
+                                 int32_t* d_order, void* stream) {
+  if (nwalkers <= 0 || !d_order) return fail(MP_ERR_BAD_ARG, "mp_ensemble_order: bad argument");
+  const SplitPerm perm = make_split_perm(nwalkers, seed, step, randomize_split);
+  order_kernel<<<(nwalkers + 255) / 256, 256, 0, (cudaStream_t)stream>>>(perm, nwalkers, d_order);
+  MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
+// ---- peer-mapped replicas (CUDA IPC) -------------------------------------------------------------
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the C ABI carries IPC handles as 64 bytes");
+
+extern "C" int mp_peer_alloc(int32_t device, uint64_t bytes, void** d_ptr, unsigned char handle[64]) {
+  if (!d_ptr || !handle || bytes == 0) return fail(MP_ERR_BAD_ARG, "mp_peer_alloc: bad argument");
+  if (mp_device_count() <= device || device < 0) return fail(MP_ERR_CUDA, "mp_peer_alloc: no such CUDA device");
+  MP_CUDA(cudaSetDevice(device));
+  void* p = nullptr;
+  MP_CUDA(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  cudaIpcMemHandle_t hd;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&hd, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    return fail(MP_ERR_CUDA, std::string("mp_peer_alloc: ") + cudaGetErrorString(e));
+  }
+  std::memcpy(handle, &hd, 64);
+  *d_ptr = p;
+  return MP_OK;
+}
+
+extern "C" int mp_peer_open(int32_t device, const unsigned char handle[64], void** d_ptr) {
+  if (!d_ptr || !handle) return fail(MP_ERR_BAD_ARG, "mp_peer_open: null pointer");
+  MP_CUDA(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  std::memcpy(&hd, handle, 64);
+  MP_CUDA(cudaIpcOpenMemHandle(d_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return MP_OK;
+}
+
+extern "C" int mp_peer_close(int32_t device, void* d_ptr) {
+  if (!d_ptr) return MP_OK;
+  MP_CUDA(cudaSetDevice(device));
+  MP_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return MP_OK;
+}
+
+extern "C" int mp_peer_free(int32_t device, void* d_ptr) {
+  if (!d_ptr) return MP_OK;
+  MP_CUDA(cudaSetDevice(device));
+  MP_CUDA(cudaFree(d_ptr));
+  return MP_OK;
+}
+
+extern "C" int mp_peer_barrier(int32_t device, uint64_t* d_my_flags, uint64_t* const* peer_flags, int32_t rank,
+                               int32_t world, uint64_t epoch, int32_t* d_error, void* stream) {
+  if (!d_my_flags || !peer_flags || world < 1 || world > MP_MAX_PEERS + 1 || rank < 0 || rank >= world)
+    return fail(MP_ERR_BAD_ARG, "mp_peer_barrier: bad argument");
+  if (world == 1) return MP_OK;
+  MP_CUDA(cudaSetDevice(device));
+  PeerFlags pf;
+  std::memset(&pf, 0, sizeof(pf));
+  for (int p = 0; p < world; ++p) {
+    if (p != rank && !peer_flags[p]) return fail(MP_ERR_BAD_ARG, "mp_peer_barrier: null peer flag array");
+    pf.p[p] = peer_flags[p];
+  }
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_my_flags, pf, rank, world, epoch, d_error);
   MP_CUDA(cudaGetLastError());
   return MP_OK;
 }
@@ -947,7 +1172,8 @@ extern "C" int mp_last_stiff_count(mp_handle* h, int32_t* count) {
   if (!h || !count) return fail(MP_ERR_BAD_ARG, "mp_last_stiff_count: null pointer");
   MP_CUDA(cudaSetDevice(h->device));
   MP_CUDA(cudaDeviceSynchronize());
-  MP_CUDA(cudaMemcpy(count, h->lanes[0].queue_count, sizeof(int), cudaMemcpyDeviceToHost));
+  const mp_handle::Lane* L = h->last_lane ? h->last_lane : &h->lanes[0];
+  MP_CUDA(cudaMemcpy(count, L->queue_count, sizeof(int), cudaMemcpyDeviceToHost));
   return MP_OK;
 }
 

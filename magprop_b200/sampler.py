@@ -10,18 +10,26 @@ so this module carries the minimum needed to run and measure the path:
                         (one kernel launch per half-step).
 ``DeviceEnsemble``      positions stay on the GPU; proposal + likelihood +
                         accept are ONE fused launch per half-step
-                        (``mp_stretch_half_step``).  With ``torch.distributed``
-                        initialised the active half is split over the ranks and
-                        the updated rows are all-gathered each half-step (NCCL
-                        over NVLink on GPUs; gloo in the CPU tests).
+                        (``mp_ensemble_half_step``).  With ``torch.distributed``
+                        initialised every rank holds a replica of the ensemble and
+                        moves its share of the active half; the moved rows reach the
+                        other replicas either by NVLink peer stores issued from the
+                        kernel's epilogue plus one flag barrier (``exchange="peer"``,
+                        no collective at all), or packed into ONE all-gather per
+                        half-step (``exchange="allgather"``; gloo in the CPU tests).
 
-Move semantics (Goodman & Weare 2010, as emcee's RedBlueMove implements them):
-for each half S with complement C:  z = ((a-1)u+1)^2/a,  q = c_j - (c_j - s) z
-with j uniform in C (with replacement),  accept iff
-(ndim-1) ln z + lp(q) - lp(s) > ln u'.   C includes the updates made by the
-first half-step of the same step.
+Move semantics (Goodman & Weare 2010, as emcee's RedBlueMove implements them;
+SURVEY.md appendix C): every step the walkers are split into two halves at random
+(``randomize_split=True``, emcee's default); for each half S with complement C:
+z = ((a-1)u+1)^2/a,  q = c_j - (c_j - s) z  with j uniform in C (with
+replacement),  accept iff  (ndim-1) ln z + lp(q) - lp(s) > ln u'.   C includes
+the updates made by the first half-step of the same step.  On the device the
+random split is a permutation keyed by (seed, step) that every thread of every
+rank evaluates on the fly (include/magprop_b200.h, ``mp_ensemble``).
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import numpy as np
 
@@ -101,81 +109,217 @@ def rank_slice(n_items: int, rank: int, world: int):
     return rank * m, (rank + 1) * m
 
 
-class DeviceEnsemble:
-    """Ensemble whose positions live on the device; fixed halves [0, n/2) and [n/2, n).
+class _RawCuda:
+    """A raw device allocation presented through ``__cuda_array_interface__`` (so torch can view it)."""
 
-    half_step(coords, lnp, active, complement, a, seed, step, accepted) must perform one
-    stretch-move half-step in place for the walkers listed in `active`.  On a GPU it is
-    ``Likelihood.stretch_half_step`` (see ``from_likelihood``); tests inject a CPU double
-    so the sharding/all-gather logic runs under gloo.
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class CudaBackend:
+    """The CUDA library as the mover of a ``DeviceEnsemble`` (``mp_ensemble_half_step`` and friends)."""
+
+    peer_capable = True
+
+    def __init__(self, lik):
+        import torch
+        from . import _capi as A
+        self.A, self.lik, self.lib, self.torch = A, lik, A.load(), torch
+        self.device = torch.device("cuda", lik.device)
+        self._own = []          # (ptr, tensor) blocks from mp_peer_alloc
+        self._opened = []       # peer mappings from mp_peer_open
+
+    def stream(self):
+        return self.torch.cuda.current_stream(self.device).cuda_stream
+
+    def alloc_shared(self, nbytes):
+        """Zeroed device memory other processes can map (CUDA IPC): (uint8 tensor view, 64-byte handle)."""
+        ptr = C.c_void_p()
+        handle = C.create_string_buffer(64)
+        self.A.check(self.lib.mp_peer_alloc(self.lik.device, nbytes, C.byref(ptr), handle))
+        t = self.torch.as_tensor(_RawCuda(ptr.value, nbytes), device=self.device)
+        self._own.append((ptr.value, t))
+        return t, handle.raw
+
+    def open_peer(self, handle: bytes) -> int:
+        ptr = C.c_void_p()
+        self.A.check(self.lib.mp_peer_open(self.lik.device, handle, C.byref(ptr)))
+        self._opened.append(ptr.value)
+        return ptr.value
+
+    def release(self):
+        for p in self._opened:
+            self.lib.mp_peer_close(self.lik.device, p)
+        self._opened = []
+        for p, _ in self._own:
+            self.lib.mp_peer_free(self.lik.device, p)
+        self._own = []
+
+    def half_step(self, ens, step, split):
+        self.A.check(self.lib.mp_ensemble_half_step(self.lik._h, C.byref(ens.desc), step, split, self.stream() or None))
+
+    def unpack(self, ens, step, split, gathered):
+        self.A.check(self.lib.mp_ensemble_unpack(C.byref(ens.desc), step, split, gathered.data_ptr(), self.stream() or None))
+
+    def barrier(self, ens, epoch):
+        self.A.check(self.lib.mp_peer_barrier(self.lik.device, ens._flags.data_ptr(), ens._peer_flag_ptrs, ens.rank,
+                                              ens.world, epoch, ens._error.data_ptr(), self.stream() or None))
+
+    def lnprob_all(self, ens):
+        self.lik.lnprob_device(ens.coords.data_ptr(), ens.nwalkers, ens.ndim, ens.lnp.data_ptr(), 0, 0, self.stream())
+
+
+class DeviceEnsemble:
+    """Ensemble whose positions live on the device (replicated on every rank of a distributed run).
+
+    ``backend`` performs the half-steps: ``CudaBackend`` on a GPU (see ``from_likelihood``); the tests inject a
+    NumPy double so the sharding / exchange logic runs under gloo on the CPU.
     """
 
-    def __init__(self, half_step, nwalkers, ndim, a=2.0, seed=0, device="cuda", dist=None):
+    BAD_CAPACITY = 4096
+
+    def __init__(self, backend, nwalkers, ndim, a=2.0, seed=0, device="cuda", dist=None, randomize_split=True,
+                 exchange="auto"):
         import torch
+        from . import _capi as A
         if nwalkers % 2 or nwalkers < 2 * ndim:
             raise ValueError("nwalkers must be even and at least 2*ndim")
-        self.torch = torch
-        self.half_step, self.nwalkers, self.ndim, self.a, self.seed = half_step, nwalkers, ndim, float(a), int(seed)
+        self.torch, self.backend = torch, backend
+        self.nwalkers, self.ndim, self.a, self.seed = nwalkers, ndim, float(a), int(seed)
+        self.randomize_split = bool(randomize_split)
         self.device = torch.device(device)
         self.dist = dist if (dist is not None and dist.is_initialized() and dist.get_world_size() > 1) else None
-        # gloo (the CPU tests) needs a separate send buffer; NCCL gathers in place
-        self.inplace_gather = bool(self.dist) and self.dist.get_backend() == "nccl"
         self.rank = self.dist.get_rank() if self.dist else 0
         self.world = self.dist.get_world_size() if self.dist else 1
         half = nwalkers // 2
         lo, hi = rank_slice(half, self.rank, self.world)
-        idx = torch.arange(nwalkers, dtype=torch.int32, device=self.device)
-        self.halves = (idx[:half].contiguous(), idx[half:].contiguous())
-        self.mine = (self.halves[0][lo:hi].contiguous(), self.halves[1][lo:hi].contiguous())
-        self.my_rows = ((lo, hi), (half + lo, half + hi))
-        self.coords = torch.empty((nwalkers, ndim), dtype=torch.float64, device=self.device)
-        self.lnp = torch.empty(nwalkers, dtype=torch.float64, device=self.device)
+        self.n_mine = hi - lo
+        if self.world - 1 > A.MP_MAX_PEERS:
+            raise ValueError(f"at most {A.MP_MAX_PEERS + 1} ranks")
+        # ---- how the moved rows travel
+        if not self.dist:
+            exchange = "none"
+        elif exchange == "auto":
+            exchange = "peer" if (getattr(backend, "peer_capable", False) and self.dist.get_backend() == "nccl") else "allgather"
+        if exchange not in ("none", "peer", "allgather"):
+            raise ValueError("exchange must be 'auto', 'peer' or 'allgather'")
+        self._peer_ptrs = []
+        self._epoch = 0
+        if exchange == "peer":
+            exchange = self._setup_peer_block()          # falls back to "allgather" if a mapping fails on any rank
+        if exchange != "peer":
+            self.coords = torch.empty((nwalkers, ndim), dtype=torch.float64, device=self.device)
+            self.lnp = torch.empty(nwalkers, dtype=torch.float64, device=self.device)
+        self.exchange = exchange
         self.accepted = torch.zeros(nwalkers, dtype=torch.int32, device=self.device)
+        self.status = torch.zeros(nwalkers, dtype=torch.int32, device=self.device)
+        self.bad_rows = torch.zeros((self.BAD_CAPACITY, ndim), dtype=torch.float64, device=self.device)
+        self.bad_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.pack = self.gathered = None
+        if exchange == "allgather":
+            self.pack = torch.empty((self.n_mine, ndim + 1), dtype=torch.float64, device=self.device)
+            self.gathered = torch.empty((half, ndim + 1), dtype=torch.float64, device=self.device)
         self.step = 0
+        # ---- the C descriptor
+        d = A.Ensemble()
+        d.coords, d.lnp = self.coords.data_ptr(), self.lnp.data_ptr()
+        d.nwalkers, d.ndim, d.a, d.seed = nwalkers, ndim, self.a, self.seed
+        d.randomize_split, d.rank, d.world = int(self.randomize_split), self.rank, self.world
+        d.accepted, d.status, d.n_rhs = self.accepted.data_ptr(), self.status.data_ptr(), None
+        d.n_peers = len(self._peer_ptrs)
+        for k, (pc, pl) in enumerate(self._peer_ptrs):
+            d.peer_coords[k], d.peer_lnp[k] = pc, pl
+        d.pack_out = self.pack.data_ptr() if self.pack is not None else None
+        d.bad_rows, d.bad_count, d.bad_capacity = self.bad_rows.data_ptr(), self.bad_count.data_ptr(), self.BAD_CAPACITY
+        self.desc = d
+
+    # -- peer-mapped replicas --------------------------------------------------------------------
+    def _setup_peer_block(self):
+        """One IPC-exportable block per rank: coords | lnp | flags[16] | error.  Every rank maps every other
+        rank's block.  Returns the exchange mode that holds on ALL ranks."""
+        t, n, ndim = self.torch, self.nwalkers, self.ndim
+        nb_c, nb_l, nb_f = n * ndim * 8, n * 8, 16 * 8
+        ok = 1
+        try:
+            block, handle = self.backend.alloc_shared(nb_c + nb_l + nb_f + 8)
+        except Exception:
+            ok, block, handle = 0, None, b""
+        handles = [None] * self.world
+        self.dist.all_gather_object(handles, handle)
+        ptrs = {}
+        if ok:
+            try:
+                for r, hd in enumerate(handles):
+                    if r != self.rank:
+                        if len(hd) != 64:
+                            raise RuntimeError("peer has no block")
+                        ptrs[r] = self.backend.open_peer(hd)
+            except Exception:
+                ok = 0
+        flag = t.tensor([ok], dtype=t.int32, device=self.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        if int(flag.item()) != 1:
+            self.backend.release()
+            return "allgather"
+        self.coords = block[:nb_c].view(t.float64).view(n, ndim)
+        self.lnp = block[nb_c:nb_c + nb_l].view(t.float64)
+        self._flags = block[nb_c + nb_l:nb_c + nb_l + nb_f].view(t.int64)
+        self._error = block[nb_c + nb_l + nb_f:].view(t.int32)
+        self._peer_ptrs = [(ptrs[r], ptrs[r] + nb_c) for r in range(self.world) if r != self.rank]
+        arr = (C.c_void_p * self.world)()
+        for r in range(self.world):
+            arr[r] = (ptrs[r] + nb_c + nb_l) if r != self.rank else None
+        self._peer_flag_ptrs = arr
+        return "peer"
 
     @classmethod
-    def from_likelihood(cls, lik, nwalkers, ndim, a=2.0, seed=0, dist=None):
+    def from_likelihood(cls, lik, nwalkers, ndim, a=2.0, seed=0, dist=None, randomize_split=True, exchange="auto"):
         import torch
-        device = torch.device("cuda", lik.device)
-
-        def half_step(coords, lnp, active, complement, a_, seed_, step_, accepted):
-            lik.stretch_half_step(coords.data_ptr(), lnp.data_ptr(), coords.shape[0], coords.shape[1],
-                                  active.data_ptr(), active.numel(), complement.data_ptr(), complement.numel(),
-                                  a_, seed_, step_, accepted.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
-
-        ens = cls(half_step, nwalkers, ndim, a=a, seed=seed, device=device, dist=dist)
+        ens = cls(CudaBackend(lik), nwalkers, ndim, a=a, seed=seed, device=torch.device("cuda", lik.device), dist=dist,
+                  randomize_split=randomize_split, exchange=exchange)
         ens._lik = lik
         return ens
 
+    def close(self):
+        """Unmap the peers' replicas and free this rank's (after every rank is done with them)."""
+        if self.exchange == "peer":
+            self.torch.cuda.synchronize(self.device)
+            self.dist.barrier()
+            self.backend.release()
+            self.exchange = "closed"
+
+    # -- state ----------------------------------------------------------------------------------------
     def set_state(self, coords, lnp):
         t = self.torch
         self.coords.copy_(t.as_tensor(np.asarray(coords), dtype=t.float64).to(self.device)
                           if not isinstance(coords, t.Tensor) else coords)
         self.lnp.copy_(t.as_tensor(np.asarray(lnp), dtype=t.float64).to(self.device)
                        if not isinstance(lnp, t.Tensor) else lnp)
+        self._sync_ranks()
 
     def initialise(self, p0):
         """Positions from p0 and their lnprob from the likelihood (GPU ensembles only)."""
         self.set_state(p0, np.zeros(self.nwalkers))
-        self._lik.lnprob_device(self.coords.data_ptr(), self.nwalkers, self.ndim, self.lnp.data_ptr(), 0, 0,
-                                self.torch.cuda.current_stream().cuda_stream)
+        self.backend.lnprob_all(self)
+        self._sync_ranks()
 
-    def _gather(self, split):
-        """All-gather this rank's updated rows of half `split` into the replicated arrays."""
-        if not self.dist:
-            return
-        half = self.nwalkers // 2
-        lo, hi = self.my_rows[split]
-        base = split * half
-        if self.inplace_gather:
-            # NCCL's in-place all-gather: this rank's rows already sit at their place in the output
-            self.dist.all_gather_into_tensor(self.coords[base:base + half], self.coords[lo:hi])
-            self.dist.all_gather_into_tensor(self.lnp[base:base + half], self.lnp[lo:hi])
-        else:
-            send_c = self.coords[lo:hi].clone()
-            send_l = self.lnp[lo:hi].clone()
-            self.dist.all_gather_into_tensor(self.coords[base:base + half], send_c)
-            self.dist.all_gather_into_tensor(self.lnp[base:base + half], send_l)
+    def _sync_ranks(self):
+        # peers store into this replica during a half-step: nobody may start one before everybody's state is in place
+        if self.exchange == "peer":
+            self.torch.cuda.synchronize(self.device)
+            self.dist.barrier()
+
+    # -- stepping ---------------------------------------------------------------------------------------
+    def _half(self, split):
+        """This rank's share of half `split` of the current step, then the exchange."""
+        self.backend.half_step(self, self.step, split)
+        if self.exchange == "peer":
+            self._epoch += 1
+            self.backend.barrier(self, self._epoch)
+        elif self.exchange == "allgather":
+            self.dist.all_gather_into_tensor(self.gathered, self.pack)
+            self.backend.unpack(self, self.step, split, self.gathered)
 
     def run(self, nsteps, store=False):
         """nsteps stretch-move steps (2 half-steps each).  Returns the chain
@@ -184,15 +328,18 @@ class DeviceEnsemble:
         chain = t.empty((nsteps, self.nwalkers, self.ndim), dtype=t.float64, device=self.device) if store else None
         lps = t.empty((nsteps, self.nwalkers), dtype=t.float64, device=self.device) if store else None
         for it in range(nsteps):
-            for split in (0, 1):
-                self.half_step(self.coords, self.lnp, self.mine[split], self.halves[1 - split], self.a, self.seed,
-                               2 * self.step + split, self.accepted)
-                self._gather(split)
+            self._half(0)
+            self._half(1)
             self.step += 1
             if store:
                 chain[it].copy_(self.coords)
                 lps[it].copy_(self.lnp)
         return (chain, lps) if store else None
+
+    def check_peers(self):
+        """Raise if a cross-GPU barrier timed out (a peer died)."""
+        if self.exchange == "peer" and int(self._error.cpu()[0]) != 0:
+            raise RuntimeError("DeviceEnsemble: a peer did not reach the half-step barrier within 10 s")
 
     def acceptance_fraction(self):
         acc = self.accepted.clone()
@@ -200,11 +347,27 @@ class DeviceEnsemble:
             self.dist.all_reduce(acc)
         return acc.double() / max(1, self.step)
 
+    def drain_bad(self):
+        """Proposals whose likelihood was not finite since the last call -- the rows the reference appends to
+        ``{GRB}_bad.csv`` (mcmc_eqns.py:72-79) -- as a NumPy array [k, ndim] (all ranks' rows on every rank).
+        Returns (rows, dropped): `dropped` counts rows beyond the device log's capacity."""
+        n = int(self.bad_count.cpu()[0])
+        rows = self.bad_rows[:min(n, self.BAD_CAPACITY)].cpu().numpy().copy()
+        dropped = max(0, n - self.BAD_CAPACITY)
+        self.bad_count.zero_()
+        if self.dist:
+            parts = [None] * self.world
+            self.dist.all_gather_object(parts, (rows, dropped))
+            rows = np.concatenate([p[0] for p in parts], axis=0)
+            dropped = sum(p[1] for p in parts)
+        return rows, dropped
+
 
 def run_concurrently(ensembles, nsteps, store=False):
     """Advance several independent device ensembles (e.g. one per dataset / burst) ``nsteps`` steps each, every
     ensemble on its own CUDA stream with the launches interleaved step by step, so that small ensembles --
     which are latency-bound, a few warps each -- share the GPU instead of queueing behind one another.
+    (Ensembles on ONE likelihood handle are fine: the library keeps a stiff queue per stream.)
     Returns a list of (chain, lnprob) per ensemble when ``store`` (else None)."""
     import torch
     streams = [torch.cuda.Stream(device=e.device) for e in ensembles]
@@ -218,10 +381,8 @@ def run_concurrently(ensembles, nsteps, store=False):
     for it in range(nsteps):
         for k, (e, st) in enumerate(zip(ensembles, streams)):
             with torch.cuda.stream(st):
-                for split in (0, 1):
-                    e.half_step(e.coords, e.lnp, e.mine[split], e.halves[1 - split], e.a, e.seed, 2 * e.step + split,
-                                e.accepted)
-                    e._gather(split)
+                e._half(0)
+                e._half(1)
                 e.step += 1
                 if store:
                     out[k][0][it].copy_(e.coords)

@@ -58,9 +58,11 @@ class RunResult:
         return integrated_time(self._chain, **kw)
 
 
-def run(grb, x, y, yerr, n_walk, n_step, seed=0, p0=None, device=0, dist=None):
+def run(grb, x, y, yerr, n_walk, n_step, seed=0, p0=None, device=0, dist=None, fbad=None):
     """One chain of ``n_step`` stretch-move steps for ``n_walk`` walkers, positions resident on the GPU
-    (one fused launch per half-step; with ``dist`` the ensemble is sharded over the ranks)."""
+    (one fused launch per half-step; with ``dist`` the ensemble is sharded over the ranks).  ``fbad``: the
+    reference's bad-parameter file (``synth_mcmc.py:159,181``, ``mcmc_eqns.py:72-79``) -- proposals whose likelihood
+    was not finite are logged on the device and appended to it after the run (by rank 0)."""
     from .. import _capi as A
     from ..engine import Likelihood, time_grid
     from ..sampler import DeviceEnsemble
@@ -75,7 +77,14 @@ def run(grb, x, y, yerr, n_walk, n_step, seed=0, p0=None, device=0, dist=None):
         ens = DeviceEnsemble.from_likelihood(lk, n_walk, p0.shape[1], a=2.0, seed=seed, dist=dist)
         ens.initialise(p0)
         chain, lnp = ens.run(n_step, store=True)
+        ens.check_peers()
         res = RunResult(chain.cpu().numpy(), lnp.cpu().numpy(), ens.acceptance_fraction().cpu().numpy(), seed)
+        bad, dropped = ens.drain_bad()
+        res.bad_rows, res.bad_dropped = bad, dropped
+        if fbad is not None and ens.rank == 0 and len(bad):
+            from .mcmc_eqns import _write_bad
+            _write_bad(fbad, bad)
+        ens.close()
     finally:
         lk.close()
     return res

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../magprop_b200/csrc/magprop_host.hpp"
+#include "../../magprop_b200/csrc/magprop_rng.cuh"
 
 using namespace mp;
 
@@ -170,4 +171,10 @@ extern "C" int hs_trace(const mp_model_spec* ms, const double* grid, int G, cons
     ++n;
   }
   return n;
+}
+
+// the ensemble order (keyed permutation) as the kernels compute it
+extern "C" void hs_ensemble_order(int n, unsigned long long seed, unsigned long long step, int randomize, int* order) {
+  const SplitPerm p = make_split_perm(n, seed, step, randomize);
+  for (int g = 0; g < n; ++g) order[g] = (int)perm_at(p, (uint32_t)g);
 }

@@ -65,3 +65,76 @@ def half_step(coords, lnp, active, complement, a, seed, step, lnprob_fn, accepte
     if accepted is not None:
         accepted[active[acc]] += 1
     return q, acc
+
+
+# ---- the ensemble order: keyed permutation of [0, n) (perm_at / make_split_perm in magprop_kernels.cu) ----
+def _mix32(x):
+    x = x & MASK
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7feb352d)) & MASK
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846ca68b)) & MASK
+    x ^= x >> np.uint64(16)
+    return x
+
+
+def ensemble_order(n, seed, step, randomize=True):
+    """order[g] = walker at position g of the ensemble order of MCMC step `step`; halves are g < n/2, g >= n/2."""
+    g = np.arange(n, dtype=np.uint64)
+    if not randomize:
+        return g.astype(np.int64)
+    hb = 1
+    while (1 << (2 * hb)) < n:
+        hb += 1
+    mask = np.uint64((1 << hb) - 1)
+    z = np.zeros(1, dtype=np.uint64)
+    k = philox4x32_10(z + np.uint64(step & 0xFFFFFFFF), z + np.uint64((step >> 32) & 0xFFFFFFFF), z, z + np.uint64(2),
+                      seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    k0, k1 = np.uint64(int(k[0][0])), np.uint64(int(k[1][0]))
+    x = g.copy()
+    todo = np.ones(n, dtype=bool)
+    while todo.any():
+        xx = x[todo]
+        L, R = xx >> np.uint64(hb), xx & mask
+        for r in range(6):
+            F = _mix32(((R + np.uint64((r * 0x9E3779B9) & 0xFFFFFFFF)) & MASK) ^ (k1 if r & 1 else k0)) & mask
+            L, R = R, L ^ F
+        xx = (L << np.uint64(hb)) | R
+        x[todo] = xx
+        todo[todo] = xx >= np.uint64(n)
+    return x.astype(np.int64)
+
+
+class NumpyBackend:
+    """CPU stand-in for ``magprop_b200.sampler.CudaBackend``: the same half-step on NumPy views of the
+    ensemble's (CPU) tensors, with the log-probability supplied by the caller."""
+
+    peer_capable = False
+
+    def __init__(self, lnprob_fn):
+        self.lnprob_fn = lnprob_fn
+
+    def _sets(self, ens, step, split):
+        n, half = ens.nwalkers, ens.nwalkers // 2
+        order = ensemble_order(n, ens.seed, step, ens.randomize_split)
+        m = half // ens.world
+        pos0 = split * half + ens.rank * m
+        return order, order[pos0:pos0 + m], order[(1 - split) * half:(1 - split) * half + half]
+
+    def half_step(self, ens, step, split):
+        coords, lnp, acc = ens.coords.numpy(), ens.lnp.numpy(), ens.accepted.numpy()
+        _, active, comp = self._sets(ens, step, split)
+        half_step(coords, lnp, active, comp, ens.a, ens.seed, 2 * step + split, self.lnprob_fn, acc)
+        if ens.pack is not None:
+            p = ens.pack.numpy()
+            p[:, :ens.ndim] = coords[active]
+            p[:, ens.ndim] = lnp[active]
+
+    def unpack(self, ens, step, split, gathered):
+        order, _, _ = self._sets(ens, step, split)
+        half = ens.nwalkers // 2
+        rows = order[split * half:split * half + half]
+        g = gathered.numpy()
+        ens.coords.numpy()[rows] = g[:, :ens.ndim]
+        ens.lnp.numpy()[rows] = g[:, ens.ndim]
+
+    def lnprob_all(self, ens):
+        ens.lnp.numpy()[:] = self.lnprob_fn(ens.coords.numpy())

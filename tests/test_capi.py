@@ -39,6 +39,24 @@ def test_struct_layouts(built):
     assert (p.inertia_factor, p.mdot_factor, p.rhs_n, p.lum_n, p.breakup_lum, p.lprop_binding_term) == (0.8, 1.0, 1.0, 7.0, 0.0, 0)
 
 
+def test_ensemble_struct_matches_the_header(built, tmp_path):
+    """mp_ensemble as ctypes lays it out == as a C compiler lays out the header's definition."""
+    import subprocess
+    from magprop_b200 import _capi as A
+    fields = [f[0] for f in A.Ensemble._fields_]
+    prog = ['#include <stdio.h>', '#include <stddef.h>', '#include "magprop_b200.h"', 'int main(void) {',
+            '  printf("%zu %d\\n", sizeof(mp_ensemble), MP_MAX_PEERS);']
+    prog += [f'  printf("%zu\\n", offsetof(mp_ensemble, {f}));' for f in fields]
+    prog += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(prog))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    assert int(out[0]) == C.sizeof(A.Ensemble) and int(out[1]) == A.MP_MAX_PEERS
+    assert [int(v) for v in out[2:]] == [getattr(A.Ensemble, f).offset for f in fields]
+
+
 def test_no_cpu_fallback(built):
     """Without a CUDA device every compute entry point must raise."""
     if has_gpu():
