@@ -1225,6 +1225,7 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   unsigned regime_trial;
   const int code = step_spin_chain(sp, w, in, t, y, h, tn, d, y_trial, regime_trial);
   if (code == 1) in.E = Eend;
+  if (in.n_steps >= sp.max_steps && in.t < t_end) in.status = kWalkerIntegratorFail;   // step budget (accepted steps count too)
   if (code == 2) {
     // locate the kink and aim the next attempt at it; one within 1e-3 of either end of the trial is
     // left alone (its effect is O(1e-6) of a full crossing): the attempt is repeated as one-sided

@@ -178,3 +178,59 @@ extern "C" void hs_ensemble_order(int n, unsigned long long seed, unsigned long 
   const SplitPerm p = make_split_perm(n, seed, step, randomize);
   for (int g = 0; g < n; ++g) order[g] = (int)perm_at(p, (uint32_t)g);
 }
+
+// Cost trace of the explicit pass (design aid for the launch scheduling): for each walker, the number of
+// step attempts it makes inside each chunk of NB nodes, whether / after how many attempts it is deferred as
+// stiff, and the implicit pass's step and RHS counts from the hand-over point.
+extern "C" int hs_cost_trace(const mp_model_spec* ms, const mp_prior_spec* pr, const double* grid, int G,
+                             const double* t, const double* y, const double* yerr, int D, const double* theta,
+                             int W, int ndim, int NB, int max_chunks, int* chunk_steps /*[W][max_chunks]*/,
+                             int* total_steps, int* deferred_at, int* stiff_steps, int* stiff_rhs) {
+  NodeProgram np;
+  int rc = build_node_program(grid, G, t, y, yerr, D, np);
+  if (rc) return rc;
+  Spec sp = make_spec(*ms);
+  const int Nn = (int)np.node_t.size();
+  const double t_end = np.node_t[Nn - 1];
+  for (int w = 0; w < W; ++w) {
+    const double* th = theta + (size_t)w * ndim;
+    int* cs = chunk_steps + (size_t)w * max_chunks;
+    for (int c = 0; c < max_chunks; ++c) cs[c] = 0;
+    total_steps[w] = 0; deferred_at[w] = -1; stiff_steps[w] = 0; stiff_rhs[w] = 0;
+    if (pr->enabled && !prior_accepts(th, ndim, pr->lower, pr->upper)) continue;
+    double pars[6], de, pe, fb;
+    unpack_theta(sp, th, ndim, pars, de, pe, fb);
+    Walker wk;
+    walker_setup(sp, pars, de, pe, fb, grid[0], wk);
+    if (wk.bad) continue;
+    Integrator in;
+    in.n_rhs = 0;
+    integrator_init<true>(sp, wk, grid[0], t_end, in);
+    int jn = 0;
+    bool deferred = false;
+    for (int c0 = 0, c = 0; c0 < Nn && !deferred; c0 += NB, ++c) {
+      const int c1 = (c0 + NB < Nn) ? c0 + NB : Nn;
+      while (jn < c1) {
+        while (jn < c1 && np.node_t[jn] <= in.t) ++jn;
+        if (jn >= c1) break;
+        if (in.status != kWalkerOk) { jn = c1; break; }
+        if (in.stiff) { deferred = true; break; }
+        integrator_step(sp, wk, t_end, in);
+        if (c < max_chunks) cs[c]++;
+        total_steps[w]++;
+      }
+      if (in.status != kWalkerOk) break;
+    }
+    if (deferred) {
+      deferred_at[w] = total_steps[w];
+      Integrator im;
+      integrator_resume(in.t, 1.0 / std::sqrt(in.omega), in.h, im);
+      while (im.t < t_end && im.status == kWalkerOk) {
+        radau_step(sp, wk, t_end, im);
+        stiff_steps[w]++;
+      }
+      stiff_rhs[w] = im.n_rhs;
+    }
+  }
+  return 0;
+}

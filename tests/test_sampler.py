@@ -197,8 +197,8 @@ def test_device_ensemble_logs_bad_proposals_and_status(built, golden):
     from magprop_b200.engine import Likelihood, time_grid
     from oracle import magprop_oracle as O
     g = golden["lnprob_script"]
-    # a step budget of 40 makes every integration "fail": each in-prior proposal is a bad row
-    lk = Likelihood(A.script_model_spec(max_steps=40), time_grid(None), g["Humped_x"], g["Humped_y"], g["Humped_yerr"],
+    # a step budget of 20 makes every integration fail: each in-prior proposal is a bad row
+    lk = Likelihood(A.script_model_spec(max_steps=20), time_grid(None), g["Humped_x"], g["Humped_y"], g["Humped_yerr"],
                     O.SCRIPT_LOWER, O.SCRIPT_UPPER)
     n = 32
     p0 = O.SYNTH_TRUTHS_LOG["Humped"] + 1e-3 * np.random.RandomState(1).randn(n, 6)
