@@ -57,6 +57,8 @@ def parse():
                          "the launch is a whole number of waves)")
     ap.add_argument("--nwalk", type=int, default=256)
     ap.add_argument("--cpu-evals", type=int, default=0, help="CPU-baseline sample size (0: ~16 per core)")
+    ap.add_argument("--curve-points", type=int, default=10 ** 6,
+                    help="parameter points of the full-grid light-curve sweep in extra.config4 (BASELINE configs[3])")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -334,9 +336,9 @@ def run_ours(args):
         dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
     e2e_value = evals_per_step * args.steps / float(e2e_dt.item())
 
-    extra = {}
+    extra, series = {}, {}
     if not args.no_extra:
-        extra = extras(args, liks, data, dev, rank, world, torch, (TRUTHS_LOG, PRIOR_LOWER, PRIOR_UPPER), A)
+        extra, series = extras(args, liks, data, dev, rank, world, torch, (TRUTHS_LOG, PRIOR_LOWER, PRIOR_UPPER), A, peak)
 
     cpu = None
     if rank == 0 and not args.no_cpu:
@@ -354,7 +356,7 @@ def run_ours(args):
         "bound": "fp64", "achieved": executed, "peak": peak, "unit": "TFLOP/s",
         "frac": executed / peak if peak else None,
         "traffic": NCU.get("dram_bytes_per_launch"),
-        "kernel": "mp::eval_kernel<kModeLnprob,64>",
+        "kernel": "mp::advance_kernel<false,64> (the explicit spin integrator; setup and reduce kernels are inside the timed launch)",
         "how": "achieved = (RHS evaluations/s, counted on the device) x (FP64 flop per RHS evaluation that the kernel "
                "executes, ncu: 2*DFMA+DMUL+DADD); peak = live DFMA micro-benchmark on this GPU (MEASURED_PEAKS.json "
                "has no FP64 entry); launch time from CUDA events on the launching stream",
@@ -377,10 +379,11 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * 6 * 8 * len(DATASETS),
                     "d2h_bytes_per_step": W * 8 * len(DATASETS)},
-            "gpu_launches": 2 * args.steps * len(DATASETS),   # eval_kernel + eval_stiff_kernel per dataset per step
+            "gpu_launches": 4 * args.steps * len(DATASETS),   # setup, advance (explicit), advance (implicit), reduce per dataset per step
             "clocks": clocks,
             "nonfinite_lnprob": bad,
             "wall_s_timed_region": wall,
+            "series": series,
             "extra": extra,
         }
         print(json.dumps(line), flush=True)
@@ -390,13 +393,20 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def extras(args, liks, data, dev, rank, world, torch, consts, A):
-    """Secondary measurements (not the headline): other ensemble shapes."""
+def extras(args, liks, data, dev, rank, world, torch, consts, A, peak):
+    """Secondary measurements (not the headline): other ensemble shapes and the other BASELINE configs."""
     TRUTHS_LOG, PRIOR_LOWER, PRIOR_UPPER = consts
-    out = {}
+    out, series = {}, {}
     rng = np.random.RandomState(99 + rank)
     lk = liks["Classic"]
     name = "Classic"
+    import torch.distributed as dist
+
+    def rank_max_ms(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def timed(theta, reps=5):
         W = theta.shape[0]
@@ -414,38 +424,51 @@ def extras(args, liks, data, dev, rank, world, torch, consts, A):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         return {"walkers": W, "ms": ms, "evals_per_s": W / ms * 1e3, "mean_rhs": float(d_n.double().mean().item()),
-                "max_rhs": int(d_n.max().item()), "stiff_bucket": lk.last_stiff_count()}
+                "max_rhs": int(d_n.max().item()), "stiff_queue": lk.last_stiff_count()}
+
+    def as_series(r, what):
+        """A first-class line for a realistic ensemble: the headline's metric with its own roofline block."""
+        executed = r["evals_per_s"] * r["mean_rhs"] * NCU["flop_per_rhs"] / 1e12
+        return {"metric": METRIC, "unit": UNIT, "value": r["evals_per_s"] * world, "per_gpu": r["evals_per_s"], "n_gpus": world,
+                "workload": what, "walkers_per_gpu": r["walkers"], "ms_per_launch": r["ms"],
+                "roofline": {"bound": "fp64", "achieved": executed, "peak": peak, "unit": "TFLOP/s",
+                             "frac": executed / peak if peak else None, "mean_rhs_per_eval": r["mean_rhs"],
+                             "flop_per_rhs_executed": NCU["flop_per_rhs"],
+                             "note": "flop per RHS from the explicit integrator's ncu capture; walkers handed to the implicit "
+                                     "integrator execute more per RHS (Jacobian, Newton solve), so this is a lower bound there"},
+                "stiff_queue": r["stiff_queue"], "max_rhs": r["max_rhs"]}
 
     truth = TRUTHS_LOG[name]
     out["config2_exact_half_step_128_walkers"] = timed(truth + 1e-4 * rng.randn(128, 6), reps=20)
     for W in (10 ** 2, 10 ** 4, 10 ** 6):
         out[f"ball_1e-4_W{W}"] = timed(truth + 1e-4 * rng.randn(W, 6))
     out["posterior_spread_0.05_W262144"] = timed(np.clip(truth + 0.05 * rng.randn(1 << 18, 6), PRIOR_LOWER, PRIOR_UPPER))
-    prior_draws = rng.uniform(PRIOR_LOWER, PRIOR_UPPER, size=(1 << 16, 6))
-    out["prior_uniform_W65536"] = timed(prior_draws, reps=1)
-    lk.set_bucketing(True)          # walkers ordered by a cost key on the device (mp_set_bucketing)
-    out["prior_uniform_W65536_bucketed"] = timed(prior_draws, reps=1)
-    out["posterior_spread_0.2_W262144_bucketed"] = timed(np.clip(truth + 0.2 * rng.randn(1 << 18, 6), PRIOR_LOWER, PRIOR_UPPER))
-    lk.set_bucketing(False)
-    out["posterior_spread_0.2_W262144"] = timed(np.clip(truth + 0.2 * rng.randn(1 << 18, 6), PRIOR_LOWER, PRIOR_UPPER))
+    r = timed(np.clip(truth + 0.2 * rng.randn(1 << 18, 6), PRIOR_LOWER, PRIOR_UPPER))
+    out["posterior_spread_0.2_W262144"] = r
+    series["posterior_spread_0.2"] = as_series(r, "Classic dataset, 262 144 walkers = log-truth + 0.2*randn clipped to the prior box "
+                                                  "(a burnt-in chain's spread)")
+    r = timed(rng.uniform(PRIOR_LOWER, PRIOR_UPPER, size=(1 << 18, 6)), reps=3)
+    out["prior_uniform_W262144"] = r
+    series["prior_uniform"] = as_series(r, "Classic dataset, 262 144 walkers uniform in the prior box of mcmc_eqns.py:40-41 "
+                                           "(burn-in / full stiffness range)")
+    out["prior_uniform_W65536"] = timed(rng.uniform(PRIOR_LOWER, PRIOR_UPPER, size=(1 << 16, 6)), reps=3)
 
-    # ---- configs[2] shape: 15 independent short-GRB fits (packaged model, "S" grid, the sample's points per
-    # burst), bursts dealt round-robin to the ranks, no communication.  Synthetic light curves on log-uniform
-    # time stamps (the k-corrected sample is not on the GPU box).
+    # ---- configs[2]: the REAL k-corrected short-GRB sample (tests/golden/sgrb_sample.npz: the reference's 15 bursts,
+    # cleaned and k-corrected by the reference's own functions), packaged model on the "S" grid, custom linear-space
+    # limits; independent fits, bursts dealt round-robin to the ranks, no communication.  Walkers: the fixture's
+    # best-fitting walker of each burst * (1 + 1e-3 randn).
     from magprop_b200.engine import Likelihood as _L, time_grid as _tg
-    d_per_grb = [253, 80, 33, 1944, 19, 8, 112, 36, 52, 214, 410, 240, 172, 151, 63]
+    sg = np.load(os.path.join(ROOT, "tests", "golden", "sgrb_sample.npz"))
     g3 = np.random.RandomState(3)
-    p3 = np.array([2.0, 3.0, 3e-3, 300.0, 1.0, 5.0])
-    lo3 = np.array([1e-3, 0.69, 1e-5, 50.0, 0.1, 1e-5]); hi3 = np.array([10.0, 10.0, 1e-1, 2000.0, 1000.0, 50.0])
-    W3, ms3, n3 = 32768, 0.0, 0
-    for i, D in enumerate(d_per_grb):
-        t3 = np.sort(10 ** g3.uniform(np.log10(0.011), np.log10(9e5), D))
-        th3 = p3 * (1 + 1e-3 * g3.randn(W3, 6))
+    W3, ms3, n3, per_burst = 32768, 0.0, 0, {}
+    for i, grb in enumerate(sg["grbs"]):
+        grb = str(grb)
+        th3 = sg[f"{grb}_theta"][0] * (1 + 1e-3 * g3.randn(W3, 6))
         if i % world != rank:
             continue
-        l0 = _L(A.packaged_model_spec(), _tg("S"), t3, np.ones(D), np.ones(D), device=dev.index)
-        y3 = l0.model_at_data(p3)[0]; l0.close()
-        l3 = _L(A.packaged_model_spec(), _tg("S"), t3, y3, 0.25 * y3, lo3, hi3, device=dev.index)
+        keep = sg[f"{grb}_keep"]
+        l3 = _L(A.packaged_model_spec(), _tg("S"), sg[f"{grb}_t"][keep], sg[f"{grb}_Lum50"][keep], sg[f"{grb}_Lum50err"][keep],
+                sg["lims_lower"][:6], sg["lims_upper"][:6], device=dev.index)
         d_t = torch.from_numpy(th3).to(dev); d_l = torch.empty(W3, dtype=torch.float64, device=dev)
         for _ in range(2):
             l3.lnprob_device(d_t.data_ptr(), W3, 6, d_l.data_ptr(), 0, 0)
@@ -455,19 +478,68 @@ def extras(args, liks, data, dev, rank, world, torch, consts, A):
         for _ in range(3):
             l3.lnprob_device(d_t.data_ptr(), W3, 6, d_l.data_ptr(), 0, 0)
         e1.record(); torch.cuda.synchronize()
-        ms3 += e0.elapsed_time(e1) / 3; n3 += W3
+        ms = e0.elapsed_time(e1) / 3
+        per_burst[grb] = {"points": int(keep.sum()), "ms": ms, "finite": int(torch.isfinite(d_l).sum().item())}
+        ms3 += ms; n3 += W3
         l3.close()
-    out["config3_sgrb_shapes_this_rank"] = {"bursts": n3 // W3, "walkers_per_burst": W3, "ms": ms3,
-                                            "evals_per_s": n3 / ms3 * 1e3 if ms3 else None,
-                                            "points_per_burst": d_per_grb, "model": "packaged, S grid"}
+    ms3_all = rank_max_ms(ms3)
+    out["config3_sgrb_sample"] = {"bursts_total": 15, "bursts_this_rank": n3 // W3, "walkers_per_burst": W3, "ms_this_rank": ms3,
+                                  "ms_max_over_ranks": ms3_all, "evals_per_s_all_ranks": 15 * W3 / ms3_all * 1e3 if ms3_all else None,
+                                  "per_burst_this_rank": per_burst, "model": "packaged, S grid, custom limits",
+                                  "data": "real: data/kcorr_sgrbs.csv + data/SGRBS/*_raw.txt via tests/golden/sgrb_sample.npz "
+                                          "(GRB 060614 cut at t <= 1e6 s)"}
 
-    # ---- fused on-device stretch move (one launch per half-step) -------------------------------
+    # ---- configs[3]: 10^6 parameter points of model_lum on the full 10 001-node grid (funcs.py:230-231), uniform in
+    # the prior box, streamed in chunks; each chunk's (Ltot, Lprop, Ldip) block stays on the device and is folded into
+    # a checksum there (240 GB of curves never cross PCIe).  The points are shared out over the ranks.
+    lkc = _L(A.script_model_spec(unlog=False), _tg(None), device=dev.index)
+    Gs = lkc.curve_nodes(1)
+    n_total = args.curve_points
+    n_mine = n_total // world + (1 if rank < n_total % world else 0)
+    chunk = 8192
+    d_out = torch.empty((chunk, 3, Gs), dtype=torch.float64, device=dev)
+    d_st = torch.empty(chunk, dtype=torch.int32, device=dev)
+    gc = np.random.RandomState(41 + rank)
+    checksum = torch.zeros((), dtype=torch.float64, device=dev)
+    nonfinite = torch.zeros((), dtype=torch.int64, device=dev)
+    failed = torch.zeros((), dtype=torch.int64, device=dev)
+    ms4, done = 0.0, 0
+    while done < n_mine:
+        n = min(chunk, n_mine - done)
+        pl = gc.uniform(PRIOR_LOWER, PRIOR_UPPER, size=(n, 6))
+        pl[:, 2:] = 10.0 ** pl[:, 2:]
+        d_p = torch.from_numpy(pl).to(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        lkc.curves_device(d_p.data_ptr(), n, 6, 1, d_out.data_ptr(), 0, d_st.data_ptr())
+        e1.record()
+        blk = d_out[:n]
+        checksum += blk.sum()
+        nonfinite += (~torch.isfinite(blk)).sum()
+        failed += ((d_st[:n] & 2) != 0).sum()
+        torch.cuda.synchronize()
+        ms4 += e0.elapsed_time(e1)
+        done += n
+    ms4_all = rank_max_ms(ms4)
+    tot = torch.stack([checksum, nonfinite.double(), failed.double()])
+    if world > 1:
+        dist.all_reduce(tot)
+    out["config4_model_grid_sweep"] = {"points": n_total, "points_this_rank": n_mine, "nodes_per_curve": Gs, "chunk": chunk,
+                                       "ms_kernels_max_over_ranks": ms4_all, "curves_per_s": n_total / ms4_all * 1e3,
+                                       "output_GB_per_s_per_gpu": n_mine * 3 * Gs * 8 / ms4 / 1e6 if ms4 else None,
+                                       "checksum_sum_of_all_curves": float(tot[0].item()), "nonfinite_values": int(tot[1].item()),
+                                       "integrator_failures": int(tot[2].item()),
+                                       "draws": "uniform in the prior box of mcmc_eqns.py:40-41 (full stiffness range)"}
+    del d_out
+    lkc.close()
+    torch.cuda.empty_cache()
+
+    # ---- fused on-device stretch move (one evaluation pipeline per half-step) -------------------------------
     from magprop_b200.sampler import DeviceEnsemble
-    import torch.distributed as dist
 
-    def mcmc(nwalk, nsteps, use_dist):
+    def mcmc(nwalk, nsteps, use_dist, exchange="auto"):
         g = np.random.RandomState(7)          # same start on every rank (the ensemble is replicated)
-        ens = DeviceEnsemble.from_likelihood(lk, nwalk, 6, a=2.0, seed=2017, dist=dist if use_dist else None)
+        ens = DeviceEnsemble.from_likelihood(lk, nwalk, 6, a=2.0, seed=2017, dist=dist if use_dist else None, exchange=exchange)
         ens.initialise(truth + 1e-4 * g.randn(nwalk, 6))
         ens.run(2)
         torch.cuda.synchronize()
@@ -478,18 +550,33 @@ def extras(args, liks, data, dev, rank, world, torch, consts, A):
         ens.run(nsteps)
         e1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if use_dist and world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        return {"nwalkers": nwalk, "steps": nsteps, "ms_per_step": ms / nsteps, "mcmc_steps_per_s": nsteps / ms * 1e3,
-                "evals_per_s": nwalk * nsteps / ms * 1e3, "acceptance": float(ens.acceptance_fraction().mean().item()),
-                "ranks": world if use_dist else 1}
+        ens.check_peers()
+        ms = rank_max_ms(e0.elapsed_time(e1)) if use_dist else e0.elapsed_time(e1)
+        res = {"nwalkers": nwalk, "steps": nsteps, "ms_per_step": ms / nsteps, "mcmc_steps_per_s": nsteps / ms * 1e3,
+               "evals_per_s": nwalk * nsteps / ms * 1e3, "acceptance": float(ens.acceptance_fraction().mean().item()),
+               "ranks": world if use_dist else 1, "exchange": ens.exchange}
+        ens.close()
+        return res
 
     out["mcmc_config2_nwalk256_fused_stretch"] = mcmc(256, 50, False)
     big = (1 << 18) * world
-    out[f"mcmc_nwalk{big}_fused_stretch_allgather" if world > 1 else f"mcmc_nwalk{big}_fused_stretch"] = mcmc(big, 5, True)
-    return out
+    if world > 1:
+        # the sharded chain must BE the single-GPU chain (both exchanges), checked here because the test box has one GPU
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from check_dist_mcmc import sharded_equals_single
+        eq = sharded_equals_single(lk, 4096, 6)
+        flag = torch.tensor([1 if all(eq.values()) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        out["sharded_equals_single"] = bool(int(flag.item()) == 1)
+        out["sharded_equals_single_detail"] = {**eq, "nwalkers": 4096, "steps": 6, "ranks": world}
+        out[f"mcmc_nwalk{big}_sharded_peer_stores"] = mcmc(big, 5, True, "peer")
+        out[f"mcmc_nwalk{big}_sharded_packed_allgather"] = mcmc(big, 5, True, "allgather")
+        # configs[4]: 10^7 walkers on one dataset, sharded over the ranks
+        n5 = 10_000_000 - 10_000_000 % (2 * world)
+        out["config5_mcmc_1e7_walkers_sharded"] = mcmc(n5, 3, True, "peer")
+    else:
+        out[f"mcmc_nwalk{big}_fused_stretch"] = mcmc(big, 5, True)
+    return out, series
 
 
 def main():

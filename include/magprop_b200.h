@@ -100,13 +100,6 @@ int mp_create(const mp_model_spec* spec, const mp_prior_spec* prior,
               int32_t device, mp_handle** out);
 void mp_destroy(mp_handle* h);
 int mp_set_prior(mp_handle* h, const mp_prior_spec* prior);
-/* Optional bucketing of the walkers of a launch by a cost key (mass flow through the disc, then disc
- * radius) so that the lanes of a warp integrate similar walkers; results are returned in the caller's
- * order.  Pays on ensembles that are spread out (prior-uniform +35 %), costs ~2 % on a tight ball: off by
- * default.  Applies to mp_lnprob_batch[_device] and mp_model_at_data launches of >= 2048 walkers.
- * (No counterpart in the reference: its Pool.map hands walkers to processes one by one.)            */
-int mp_set_bucketing(mp_handle* h, int32_t enabled);
-
 /* ---- the hot path ----------------------------------------------------------
  * lnprob for W walkers in one launch: replaces  [lnprob(theta_i, x, y, yerr, fbad)
  * for i in walkers]  (mcmc_eqns.py:52-81; emcee's compute_log_prob with

@@ -121,7 +121,6 @@ def declare(lib):
     lib.mp_destroy.argtypes = [vp]
     lib.mp_destroy.restype = None
     lib.mp_set_prior.argtypes = [vp, C.POINTER(PriorSpec)]
-    lib.mp_set_bucketing.argtypes = [vp, C.c_int32]
     lib.mp_lnprob_batch.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
     lib.mp_lnprob_batch_async.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp, vp]
     lib.mp_synchronize.argtypes = [vp]
@@ -148,7 +147,7 @@ def declare(lib):
 
 
 EXPORTS = ["mp_abi_version", "mp_device_count", "mp_last_error", "mp_create", "mp_destroy",
-           "mp_set_prior", "mp_set_bucketing", "mp_lnprob_batch", "mp_lnprob_batch_async", "mp_synchronize", "mp_lnprob_batch_device", "mp_model_at_data",
+           "mp_set_prior", "mp_lnprob_batch", "mp_lnprob_batch_async", "mp_synchronize", "mp_lnprob_batch_device", "mp_model_at_data",
            "mp_curve_nodes", "mp_model_curves", "mp_model_curves_device", "mp_rhs_batch",
            "mp_stretch_half_step", "mp_fp64_peak_tflops", "mp_last_stiff_count",
            "mp_ensemble_half_step", "mp_ensemble_unpack", "mp_ensemble_order",

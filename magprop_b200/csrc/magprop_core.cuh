@@ -1460,213 +1460,192 @@ MP_HD void unpack_theta(const Spec& sp, const double* theta, int ndim, double* p
 }
 
 
-// ---- one walker, end to end -----------------------------------------------------
+// ---- one walker, in three stages ------------------------------------------------------------------
+// A likelihood evaluation is cut where its work changes character:
+//   1 setup      prior test, theta -> physical parameters, per-walker constants, initial step size.  Same
+//                work for every walker: one thread each, no divergence.                   (prepare_walker)
+//   2 advance    the spin integration.  The ONLY stage whose cost differs between walkers (40 .. 10^3 steps
+//                over the prior box, and an implicit integrator for the stiff ones): the kernels run it with
+//                every lane pulling its next walker off a work queue the moment its current one is done, so a
+//                warp's lanes all step on every trip whatever the spread of the ensemble.  Its product is the
+//                state at the grid nodes the data need, dropped from the dense output into ybuf[walker][node].
+//                                                        (integrator_load / integrator_step / drain_nodes)
+//   3 reduce     luminosity at those nodes, interpolation onto the data, chi-square (or the model / light-curve
+//                output).  Again the same work for every walker.                              (reduce_rows)
+// The host simulator of the tests runs the three stages back to back for one walker at a time.
 enum EvalMode { kModeLnprob = 0, kModeModelAtData = 1, kModeCurves = 2 };
 
-// Integrates the spin equation across the nodes of `dv`, NB nodes at a time:
-//   phase A  advance the integrator, dropping omega(node) from the dense output
-//            into buf[(j - c0) * bstride]            (divergent, but tiny)
-//   phase B  luminosity at the buffered nodes, interpolation onto the data and
-//            chi-square / model output               (converged across a warp:
-//            every lane walks the same node and datum indices)
-// Returns chi-square (kModeLnprob).  out/state_out semantics per mode:
-//   kModeModelAtData : out[dat_orig[i]*ostride] = model at sorted datum i (/1e50)
-//   kModeCurves      : out[(c*Gs + j)*ostride]  = Ltot,Lprop,Ldip (c=0,1,2) at node j (/1e50)
-//                      state_out[(c*Gs + j)*ostride] = Mdisc, omega (optional)
-// STIFF = false builds the explicit-only variant: a walker whose spin equation turns stiff is
-// not integrated implicitly here but returned with kWalkerDeferred, to be re-run by the
-// STIFF = true variant (the kernels bucket such walkers into a second launch, so the common
-// explicit path is compiled without the implicit integrator's register and stack footprint).
-// `live` = false makes the lane a bystander: it computes nothing but still takes part in the
-// warp votes of phase A.  Every lane of a warp must call this function (the kernels pass
-// live = false for lanes without a walker) -- see the note on convergence below.
-#if defined(__CUDA_ARCH__)
-#define MP_WARP_ANY(pred) __any_sync(0xffffffffu, (pred))
-#else
-#define MP_WARP_ANY(pred) (pred)
-#endif
-
-// Hand-over of a walker that turned stiff (lnprob / model-at-data modes): the explicit variant records where it
-// stopped -- time, state, step size, the node/datum cursors, the partial chi-square and the nodes of the
-// current chunk already evaluated -- in the next free record of `sink` (kResumeDoubles + NB doubles, claimed with
-// one atomic increment of the queue counter, so nothing is staged per thread), and the implicit variant picks
-// the integration up from `rec_in` instead of starting over (44 % of its steps, measured on prior draws).
-constexpr int kResumeDoubles = 9;    // t, y, h, chi2, Lprev, chunk start, node cursor, datum cursor, n_rhs
-struct ResumeSink {
-  int* count;        // queue counter: the record index is its value before the increment (null: no hand-over)
-  double* base;      // records, (kResumeDoubles + NB) doubles each
-  int slot;          // out: the record / queue slot claimed by this walker
+struct WalkerRec {
+  Walker w;
+  double y0, h0, k1;     // explicit integrator at t_start: y = omega^-2, first step size, dy/dt
+  unsigned regime0;      // spin_g's regime bits there
+  int status;            // kWalkerPriorReject | kWalkerNonfiniteState | kWalkerIntegratorFail, or 0: to be integrated
+  int n_rhs;             // right-hand-side evaluations spent so far
+  int pad_;
 };
-template <int MODE, int NB, bool STIFF>
-MP_HD double evaluate_walker(const Spec& sp, const DataView& dv, const Walker& w, bool live, double* buf,
-                             int bstride, int& status, int& n_rhs, double* out,
-                             double* state_out, int ostride, const int* dat_orig, void* warp_scratch,
-                             ResumeSink* sink = nullptr, const double* rec_in = nullptr) {
-  const int Nn = dv.n_nodes;
-  n_rhs = 0;
-  if (Nn <= 0) return 0.0;
-  const double t_end = ldd(dv.node_t + (Nn - 1));
+
+// A walker on its way from the explicit to the implicit integrator (or, for a spec the explicit step does
+// not implement, from setup straight to the implicit one).
+struct StiffRec {
+  double t, y, h;        // time, y = omega^-2 there, the step size in use
+  int wid, jn;           // walker, node cursor
+  int n_rhs, n_steps;
+};
+
+MP_HD void prepare_walker(const Spec& sp, const double* theta, int ndim, bool use_prior, const double* lower,
+                          const double* upper, double t_start, double t_end, WalkerRec& r) {
+  r.status = kWalkerOk;
+  r.n_rhs = 0;
+  r.y0 = r.h0 = r.k1 = 0.0;
+  r.regime0 = 0u;
+  r.pad_ = 0;
+  if (use_prior && !prior_accepts(theta, ndim, lower, upper)) {   // mcmc_eqns.py:66-69: the model is skipped
+    r.status = kWalkerPriorReject;
+    return;
+  }
+  double pars[6], dipeff, propeff, f_beam;
+  unpack_theta(sp, theta, ndim, pars, dipeff, propeff, f_beam);
+  walker_setup(sp, pars, dipeff, propeff, f_beam, t_start, r.w);
+  if (r.w.bad) {
+    r.status = kWalkerNonfiniteState;
+    return;
+  }
   Integrator in;
-  in.status = kWalkerOk;
   in.n_rhs = 0;
+  if (sp.bucciantini) {
+    // the explicit step does not carry this torque: the walker starts in the implicit integrator
+    integrator_init<false>(sp, r.w, t_start, t_end, in);
+    r.y0 = 1.0 / (in.omega * in.omega);
+  } else {
+    integrator_init<true>(sp, r.w, t_start, t_end, in);
+    r.y0 = in.omega;
+  }
+  r.h0 = in.h;
+  r.k1 = in.k1;
+  r.regime0 = in.regime;
+  r.n_rhs = in.n_rhs;
+  if (in.status != kWalkerOk) r.status = kWalkerIntegratorFail;
+}
+
+// The explicit integrator as prepare_walker left it.
+MP_HD void integrator_load(const WalkerRec& r, double t_start, Integrator& in) {
+  in.t = t_start;
+  in.omega = r.y0;
+  in.h = r.h0;
+  in.k1 = r.k1;
+  in.facold = 1.0e-4f;
+  in.rejected = 0;
+  in.n_rhs = r.n_rhs;
+  in.n_steps = 0;
+  in.status = kWalkerOk;
   in.stiff = 0;
-  in.t = dv.t_start;
-  const bool integrate = live && !w.bad;
-  if (live && w.bad) status |= kWalkerNonfiniteState;
-  int jn = 0, idat = 0, c_start = 0;
+  in.stiff_votes = 0;
+  in.have0 = 0;
+  in.J0 = in.d0_qa = in.d0_ni = 0.0;
+  in.E = 1.0;
+  in.regime = r.regime0;
+  in.h_resume = 0.0;
+  in.t0 = t_start; in.hs = 1.0;
+  in.r1 = r.y0; in.r2 = in.r3 = in.r4 = in.r5 = 0.0;
+}
+
+// The implicit integrator taking a walker over at a StiffRec.
+MP_HD void integrator_load_stiff(const StiffRec& q, Integrator& in) {
+  integrator_resume(q.t, rsqrt_fast(q.y), q.h, in);
+  in.n_rhs = q.n_rhs;
+  in.n_steps = q.n_steps;
+}
+
+// Drop the state at every node the last accepted step covers into row[] (as y = omega^-2 whichever
+// integrator produced it); returns the new node cursor.
+// (row[j * rstride] is node j: the kernels lay ybuf out per dataset size, see Work in magprop_kernels.cu)
+template <bool STIFF>
+MP_HD int drain_nodes(const Integrator& in, int jn, int Nn, const double* node_t, double* row, size_t rstride = 1) {
+  if (jn >= Nn) return jn;
+  double tn = ldd(node_t + jn);
+  if (!(tn <= in.t)) return jn;
+  const double ihs = 1.0 / in.hs;
+  do {
+    const double v = dense_eval_r(in, tn, ihs);
+    row[jn * rstride] = STIFF ? 1.0 / (v * v) : v;
+    if (++jn >= Nn) break;
+    tn = ldd(node_t + jn);
+  } while (tn <= in.t);
+  return jn;
+}
+
+// Luminosity stage at one node of one walker (state y = omega^-2 from ybuf): what stage 3 evaluates per node.
+MP_HD Lum node_luminosity(const Spec& sp, const Walker& w, double tn, double t_start, double v, bool need_mass,
+                          double& M, double& om) {
+  if (w.bad) {                                   // unphysical constants: no solution beyond the initial node
+    M = (tn == t_start) ? w.M_init : NAN;
+    om = (tn == t_start) ? w.omega0 : NAN;
+  } else {
+    M = (sp.lum_dipole_only && !need_mass) ? 0.0 : disc_mass(w, tn);
+    om = rsqrt_pos(v);                           // ~1 ulp; NaN for a failed walker's NaN
+  }
+  return luminosity(sp, w, M, om);
+}
+
+// Stage 3 for one walker, one node after the other (the form a thread runs when every thread of the warp has
+// a walker of its own -- all lanes walk the same node and datum indices, so the loop is converged).
+//   kModeLnprob      returns chi-square
+//   kModeModelAtData out[dat_orig[i]*ostride] = model at sorted datum i (/1e50)
+//   kModeCurves      out[(c*Nn + j)*ostride] = Ltot, Lprop, Ldip (c = 0,1,2), state_out likewise Mdisc, omega
+template <int MODE>
+MP_HD double reduce_rows(const Spec& sp, const DataView& dv, const Walker& w, const double* row, double* out,
+                         double* state_out, int ostride, const int* dat_orig, size_t rstride = 1) {
+  const int Nn = dv.n_nodes;
   double chi2 = 0.0, Lprev = 0.0;
-  const bool resume = STIFF && rec_in != nullptr && integrate;
-  if (resume) {
-    integrator_resume(rec_in[0], 1.0 / sqrt(rec_in[1]), rec_in[2], in);
-    chi2 = rec_in[3]; Lprev = rec_in[4];
-    c_start = (int)rec_in[5]; jn = (int)rec_in[6]; idat = (int)rec_in[7];
-    in.n_rhs = (int)rec_in[8];
-    for (int k = 0; k < jn - c_start; ++k) buf[k * bstride] = 1.0 / sqrt(rec_in[kResumeDoubles + k]);
-  } else if (integrate) {
-    integrator_init<!STIFF>(sp, w, dv.t_start, t_end, in);
-  }
-  bool deferred = false;
-  for (int c0 = 0; c0 < Nn; c0 += NB) {
-    const int c1 = (c0 + NB < Nn) ? c0 + NB : Nn;
-    const bool chunk_on = c0 >= c_start;   // (resumed walker: earlier chunks were completed by the explicit variant;
-                                           //  the lane still takes part in the warp votes of those chunks)
-    // ---- phase A
-    // (the buffer holds the integrator's state variable at the nodes -- omega, or omega^-2 from the
-    // explicit variant; a walker with unphysical constants has no solution and is patched in phase B)
-    if (live && w.bad && chunk_on) jn = c1;
-    // Each trip: (1) drain every node the current dense segment covers -- cheap, divergent;
-    // (2) one integrator step for every lane that still needs one.  The vote between the two is
-    // what keeps the warp converged for the expensive part: without it the lanes that did / did
-    // not have a node to drain run the step one group after the other (measured 10x slower), and
-    // if a node cost a trip of its own the lanes would sit out each other's steps (measured: 197
-    // step bodies per warp for 142 steps per lane).
-    for (;;) {
-      bool step = false;
-      if (integrate && !deferred && chunk_on && jn < c1) {
-        double tn = ldd(dv.node_t + jn);
-        if (tn <= in.t) {
-          const double ihs = 1.0 / in.hs;
-          do {
-            buf[(jn - c0) * bstride] = dense_eval_r(in, tn, ihs);
-            if (++jn >= c1) break;
-            tn = ldd(dv.node_t + jn);
-          } while (tn <= in.t);
-        }
-        if (jn < c1) {
-          if (in.status != kWalkerOk) {
-            for (; jn < c1; ++jn) buf[(jn - c0) * bstride] = NAN;
-          } else if (in.stiff && !STIFF) {
-            deferred = true;              // handed to the stiff-capable launch
-            if (sink && sink->count) {
-#if defined(__CUDA_ARCH__)
-              sink->slot = atomicAdd(sink->count, 1);
-#else
-              sink->slot = (*sink->count)++;
-#endif
-              double* rec_out = sink->base + (size_t)sink->slot * (kResumeDoubles + NB);
-              rec_out[0] = in.t; rec_out[1] = in.omega; rec_out[2] = in.h; rec_out[3] = chi2; rec_out[4] = Lprev;
-              rec_out[5] = (double)c0; rec_out[6] = (double)jn; rec_out[7] = (double)idat; rec_out[8] = (double)in.n_rhs;
-              for (int k = 0; k < jn - c0; ++k) rec_out[kResumeDoubles + k] = buf[k * bstride];
-            }
-          } else {
-            step = true;
-          }
-        }
-      }
-      if (!MP_WARP_ANY(step)) break;
-      if (step) {
-        if (STIFF) radau_step(sp, w, t_end, in);
-        else integrator_step(sp, w, t_end, in);
-      }
-    }
-#if defined(__CUDA_ARCH__)
+  int idat = 0;
+  for (int j = 0; j < Nn; ++j) {
+    const double tn = ldd(dv.node_t + j);
+    double M, om;
+    const Lum L = node_luminosity(sp, w, tn, dv.t_start, row[j * rstride], MODE == kModeCurves && state_out, M, om);
     if (MODE == kModeCurves) {
-      // ---- phase B, curve output: transposed.  The warp takes its 32 walkers one at a time and
-      // evaluates that walker's luminosity stage with one NODE per lane, so the three output rows
-      // (and the state rows) are written as 256-byte runs along the node axis instead of 8-byte
-      // writes 3*Gs*8 bytes apart.  Same work as the lane-per-walker form, coalesced stores.
-      const unsigned FULL = 0xffffffffu;
-      const int lane = threadIdx.x & 31;
-      Walker* sw = static_cast<Walker*>(warp_scratch);
-      unsigned srcmask = __ballot_sync(FULL, live && !deferred);
-      while (srcmask) {
-        const int src = __ffs(srcmask) - 1;
-        srcmask &= srcmask - 1;
-        if (lane == src) *sw = w;
-        double* o = reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(out), src));
-        double* so = reinterpret_cast<double*>(__shfl_sync(FULL, reinterpret_cast<unsigned long long>(state_out), src));
-        __syncwarp();
-        const int j = c0 + lane;
-        if (j < c1) {
-          const double tn = ldd(dv.node_t + j);
-          const double v = buf[lane * bstride + (src - lane)];         // column of lane `src`, row `lane`
-          const double om = sw->bad ? ((tn == dv.t_start) ? sw->omega0 : NAN) : (STIFF ? v : rsqrt_pos(v));
-          const double M = sw->bad ? ((tn == dv.t_start) ? sw->M_init : NAN)
-                                   : ((sp.lum_dipole_only && !so) ? 0.0 : disc_mass(*sw, tn));
-          const Lum L = luminosity(sp, *sw, M, om);
-          o[j] = L.tot * 1.0e-50;            // (/1e50, funcs.py:231,236, as one multiplication: <= 1 ulp)
-          o[Nn + j] = L.prop * 1.0e-50;
-          o[2 * Nn + j] = L.dip * 1.0e-50;
-          if (so) {
-            so[j] = M;
-            so[Nn + j] = om;
-          }
-        }
-        __syncwarp();
+      out[(0 * Nn + j) * ostride] = L.tot * 1.0e-50;            // (/1e50, funcs.py:231,236, as one multiplication: <= 1 ulp)
+      out[(1 * Nn + j) * ostride] = L.prop * 1.0e-50;
+      out[(2 * Nn + j) * ostride] = L.dip * 1.0e-50;
+      if (state_out) {
+        state_out[(0 * Nn + j) * ostride] = M;
+        state_out[(1 * Nn + j) * ostride] = om;
       }
-      continue;
-    }
-#endif
-    if (!live || deferred || !chunk_on) continue;
-    // ---- phase B
-    for (int j = c0; j < c1; ++j) {
-      const double v = buf[(j - c0) * bstride];
-      const double tn = ldd(dv.node_t + j);
-      double M, om;
-      if (w.bad) {
-        M = (tn == dv.t_start) ? w.M_init : NAN;
-        om = (tn == dv.t_start) ? w.omega0 : NAN;
-      } else {
-        M = (sp.lum_dipole_only && !(MODE == kModeCurves && state_out)) ? 0.0 : disc_mass(w, tn);
-        om = STIFF ? v : rsqrt_pos(v);       // ~1 ulp; NaN for a failed walker's NaN
-      }
-      const Lum L = luminosity(sp, w, M, om);
-      if (MODE == kModeCurves) {
-        out[(0 * Nn + j) * ostride] = L.tot * 1.0e-50;
-        out[(1 * Nn + j) * ostride] = L.prop * 1.0e-50;
-        out[(2 * Nn + j) * ostride] = L.dip * 1.0e-50;
-        if (state_out) {
-          state_out[(0 * Nn + j) * ostride] = M;
-          state_out[(1 * Nn + j) * ostride] = om;
+    } else {
+      while (idat < dv.n_data) {
+        const int lo = dv.dat_lo[idat];
+        const double dx = ldd(dv.dat_dx + idat);
+        const int hi = lo + (dx != 0.0 ? 1 : 0);
+        if (hi > j) break;
+        double mod;
+        if (dx == 0.0) {
+          mod = L.tot;                                   // datum sits on a grid node
+        } else {
+          mod = fma(L.tot - Lprev, ldd(dv.dat_w + idat), Lprev);   // np.interp: slope*(x-x_lo)+y_lo
         }
-      } else {
-        while (idat < dv.n_data) {
-          const int lo = dv.dat_lo[idat];
-          const double dx = ldd(dv.dat_dx + idat);
-          const int hi = lo + (dx != 0.0 ? 1 : 0);
-          if (hi > j) break;
-          double mod;
-          if (dx == 0.0) {
-            mod = L.tot;                                   // datum sits on a grid node
-          } else {
-            mod = fma(L.tot - Lprev, ldd(dv.dat_w + idat), Lprev);   // np.interp: slope*(x-x_lo)+y_lo
-          }
-          if (MODE == kModeLnprob) {
-            const double r = fma(-mod, ldd(dv.dat_c + idat), ldd(dv.dat_ys + idat));   // (y - mod/1e50)/yerr
-            chi2 = fma(r, r, chi2);
-          } else {
-            out[(dat_orig ? dat_orig[idat] : idat) * ostride] = mod * 1.0e-50;
-          }
-          ++idat;
+        if (MODE == kModeLnprob) {
+          const double r = fma(-mod, ldd(dv.dat_c + idat), ldd(dv.dat_ys + idat));   // (y - mod/1e50)/yerr
+          chi2 = fma(r, r, chi2);
+        } else {
+          out[(dat_orig ? dat_orig[idat] : idat) * ostride] = mod * 1.0e-50;
         }
-        Lprev = L.tot;
+        ++idat;
       }
+      Lprev = L.tot;
     }
   }
-  if (deferred) status |= kWalkerDeferred;
-  status |= in.status;
-  n_rhs = in.n_rhs;
   return chi2;
+}
+
+// lnlike from chi-square and the status so far (mcmc_eqns.py:22-25, 72-79); never NaN.
+MP_HD double lnlike_of(double chi2, int& status) {
+  double ll = -0.5 * chi2;                           // mcmc_eqns.py:25
+  if (status & kWalkerIntegratorFail) {
+    ll = -INFINITY;                                  // 'flag' -> -inf (mcmc_eqns.py:22-23)
+  } else if (!isfinite(ll)) {
+    status |= kWalkerNonfiniteLnlike;                // mcmc_eqns.py:72-79
+    ll = -INFINITY;
+  }
+  return ll;
 }
 
 }  // namespace mp

@@ -1,16 +1,19 @@
 // magprop_kernels.cu -- sm_100a kernels and the C ABI of include/magprop_b200.h.
 //
-// Kernels (one walker per thread, FP64 throughout, no tensor cores -- the path
-// is a scalar ODE solve, not a contraction):
-//   eval_kernel<kModeLnprob>      prior -> spin ODE -> luminosity -> interp -> chi2 -> lnprob
-//   eval_kernel<kModeModelAtData> same, writes the model at the data times
-//   eval_kernel<kModeCurves>      same, writes Ltot/Lprop/Ldip (and state) at grid nodes
-//   stretch_kernel                emcee stretch-move proposal + the above + accept, fused
-//   rhs_kernel                    the coupled reference RHS for ODEs()/odes() callers
-//   dfma_peak_kernel              FP64 FMA roofline denominator
+// FP64 throughout, no tensor cores -- the path is a scalar ODE solve per walker, not a contraction.
+// One likelihood evaluation runs as a short pipeline of launches on one stream:
+//   setup_kernel      prior -> parameters -> per-walker constants -> initial step      one thread per walker
+//   advance_kernel    the spin integration (Dormand-Prince 5(4), dense output at the   persistent warps; every lane
+//                     nodes the data need); stiff walkers are queued for ...            pulls its next walker off a
+//   advance_kernel<STIFF>  ... the implicit (Radau IIA) integrator                      queue when its own is done
+//   reduce_*_kernel   luminosity -> interpolation -> chi-square -> lnprob (or model /  thread per walker, or a warp
+//                     light-curve output; or the stretch move's accept step)           per walker with a shuffle-
+//                                                                                       reduced chi-square
+// plus rhs_kernel (the coupled reference RHS for ODEs()/odes() callers), the ensemble-order and peer-barrier
+// helpers of the device-resident sampler, and dfma_peak_kernel (FP64 FMA roofline denominator).
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -23,185 +26,40 @@
 
 namespace mp {
 
-#ifndef MP_KNB
-#define MP_KNB 16
-#endif
-constexpr int kNB = MP_KNB;  // nodes buffered per thread between phase A and phase B
-constexpr int kResumeLen = kResumeDoubles + kNB;   // one hand-over record (see evaluate_walker)
-// curve output hands one node to each lane of the warp in phase B, so it buffers a full warp's worth
-template <int MODE> struct NodeBuf { static constexpr int n = (MODE == kModeCurves) ? 32 : kNB; };
+constexpr unsigned kFull = 0xffffffffu;
 
-struct KernelArgs {
+// What every stage of a launch needs to know (passed by value in the kernel parameters).
+struct Problem {
   Spec sp;
-  DataView dv;
+  DataView dv;          // nodes (+ the dataset for lnprob / model-at-data)
   const int* dat_orig;  // sorted datum -> caller's index (kModeModelAtData)
   double lower[MP_MAX_NDIM], upper[MP_MAX_NDIM];
   int prior_enabled;
   int ndim;
-  int W;
-  const double* theta;  // [W][ndim]
-  double* lnp;          // [W]
-  int* status;          // [W] or null
-  int* n_rhs;           // [W] or null
-  double* out;          // mode-dependent
-  double* state;        // curves: [W][2][Gs] or null
-  const int* order;     // [W] or null: thread i evaluates walker order[i] (walkers bucketed by a cost key)
-  int lanes_per_walker; // curve output: one walker per this many lanes (1, 2, .. 32), see launch_eval
-  int* queue;           // [W] walkers deferred to the stiff launch
-  int* queue_count;     // [1]
-  double* resume;       // [queue capacity][kResumeLen] hand-over records of the deferred walkers, or null
 };
 
-// Coalesced load of this block's walker parameters into shared memory
-// (theta rows are 48..72 B apart, so per-thread row reads would be 8-byte
-// gathers).
-template <int BLOCK>
-__device__ __forceinline__ void stage_theta(const double* __restrict__ theta, int W, int ndim,
-                                            double* s_theta, const int* __restrict__ order, int lpw) {
-  if (order || lpw > 1) {      // bucketed launch / sparse warps: each thread gathers its own row
-    const int slot = blockIdx.x * BLOCK + threadIdx.x;
-    const int i = slot / lpw;
-    const bool have = (i < W) && (slot % lpw == 0);
-    const long long w = have ? (order ? order[i] : i) : 0;
-    for (int d = 0; d < ndim; ++d) s_theta[threadIdx.x * ndim + d] = have ? theta[w * ndim + d] : 0.0;
-    __syncthreads();
-    return;
-  }
-  const long long base = (long long)blockIdx.x * BLOCK * ndim;
-  const long long total = (long long)W * ndim;
-  for (int i = threadIdx.x; i < BLOCK * ndim; i += BLOCK) {
-    const long long g = base + i;
-    s_theta[i] = (g < total) ? theta[g] : 0.0;
-  }
-  __syncthreads();
-}
+// Device work space of one launch (a slab of walkers), owned by the handle's lane.  Layouts follow the readers:
+//   recs   the stage-1 records as a structure of arrays -- 8-byte word k of walker i at recs[k*stride + i] -- so
+//          that the one-thread-per-walker kernels read and write them coalesced
+//   ybuf   node j of walker i at ybuf[i*ws + j*ns]: walker-minor (ws = 1, ns = stride) when stage 3 runs one
+//          thread per walker (small datasets), node-minor (ws = Nn, ns = 1) when it runs one warp per walker
+struct Work {
+  int W;               // walkers in the slab
+  int stride;          // slab capacity
+  size_t ws, ns;
+  unsigned long long* recs;
+  double* ybuf;        // stage 2 -> stage 3: y = omega^-2 at the nodes
+  int* status;         // [W]
+  int* n_rhs;          // [W]
+  int* work;           // [W] walkers for the explicit integrator
+  StiffRec* squeue;    // [W] walkers for the implicit integrator
+  int* counters;       // [0] walkers in `work`, [1] next to hand out, [2] walkers in `squeue`, [3] next to hand out
+};
 
-// The dataset a block works against -- node times and, per datum, y/yerr, 1e-50/yerr, x - t_lo, the
-// interpolation weight and the lower-node index -- staged in shared memory when it fits the budget below
-// (the synthetic datasets take 2.2 KB; a 1944-point burst stays in global memory behind L1).
-constexpr int kDataSmemDoubles = 768;      // 6 KB per block
-__device__ __forceinline__ bool stage_data(const DataView& g, DataView& s, double* buf, int nthreads) {
-  const int Nn = g.n_nodes, D = g.n_data;
-  const int need = Nn + 4 * D + (D + 1) / 2;
-  if (need > kDataSmemDoubles) return false;
-  double* p = buf;
-  double* nt = p; p += Nn;
-  double* ys = p; p += D;
-  double* c = p; p += D;
-  double* dx = p; p += D;
-  double* w = p; p += D;
-  int* lo = reinterpret_cast<int*>(p);
-  for (int i = threadIdx.x; i < Nn; i += nthreads) nt[i] = g.node_t[i];
-  for (int i = threadIdx.x; i < D; i += nthreads) {
-    ys[i] = g.dat_ys[i]; c[i] = g.dat_c[i]; dx[i] = g.dat_dx[i]; w[i] = g.dat_w[i]; lo[i] = g.dat_lo[i];
-  }
-  s = g;
-  s.node_t = nt; s.dat_ys = ys; s.dat_c = c; s.dat_dx = dx; s.dat_w = w; s.dat_lo = lo;
-  return true;
-}
-
-#ifndef MP_MIN_BLOCKS_32
-#define MP_MIN_BLOCKS_32 16
-#endif
-#ifndef MP_MIN_BLOCKS_64
-#define MP_MIN_BLOCKS_64 8
-#endif
-
-// One walker, end to end.  Returns true when the walker was deferred to the stiff launch.
-// `have` = false: this lane has no walker; it still walks through evaluate_walker as a bystander
-// because the warp votes there need every lane.
-template <int MODE, int BLOCK, bool STIFF>
-__device__ __forceinline__ bool eval_one(const KernelArgs& a, const DataView& dv, bool have, int w, const double* th, double* s_buf,
-                                         void* warp_scratch, ResumeSink* sink = nullptr, const double* rec_in = nullptr) {
-  int st = kWalkerOk, nr = 0;
-  double result = -INFINITY;
-  const bool rejected = have && a.prior_enabled && !prior_accepts(th, a.ndim, a.lower, a.upper);
-  if (rejected) st = kWalkerPriorReject;           // mcmc_eqns.py:66-69: model is skipped
-  const bool live = have && !rejected;
-  {
-    double pars[6], dipeff, propeff, f_beam;
-    unpack_theta(a.sp, th, a.ndim, pars, dipeff, propeff, f_beam);
-    Walker wk;
-    walker_setup(a.sp, pars, dipeff, propeff, f_beam, dv.t_start, wk);
-    double* out = nullptr;
-    double* state = nullptr;
-    if (MODE == kModeCurves) {
-      out = a.out + (size_t)w * 3 * dv.n_nodes;
-      state = a.state ? a.state + (size_t)w * 2 * dv.n_nodes : nullptr;
-    } else if (MODE == kModeModelAtData) {
-      out = a.out + (size_t)w * dv.n_data;
-    }
-    const double chi2 = evaluate_walker<MODE, NodeBuf<MODE>::n, STIFF>(a.sp, dv, wk, live, s_buf + threadIdx.x, BLOCK, st, nr,
-                                                          out, state, 1, a.dat_orig, warp_scratch,
-                                                          MODE == kModeCurves ? nullptr : sink,
-                                                          MODE == kModeCurves ? nullptr : rec_in);
-    if (!STIFF && (st & kWalkerDeferred)) return true;
-    if (live && MODE == kModeLnprob) {
-      double ll = -0.5 * chi2;                     // mcmc_eqns.py:25
-      if (st & kWalkerIntegratorFail) {
-        ll = -INFINITY;                            // 'flag' -> -inf (mcmc_eqns.py:22-23)
-      } else if (!isfinite(ll)) {
-        st |= kWalkerNonfiniteLnlike;              // mcmc_eqns.py:72-79
-        ll = -INFINITY;
-      }
-      result = ll;                                 // + lnprior == 0.0
-    }
-  }
-  if (!have) return false;
-  if (MODE == kModeLnprob) a.lnp[w] = result;
-  if (a.status) a.status[w] = st;
-  if (a.n_rhs) a.n_rhs[w] = nr;
-  return false;
-}
-
-// Main launch: explicit integrator only; stiff walkers are pushed onto a queue.
-template <int MODE, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64))
-eval_kernel(const __grid_constant__ KernelArgs a) {
-  __shared__ double s_buf[NodeBuf<MODE>::n * BLOCK];
-  __shared__ double s_theta[BLOCK * MP_MAX_NDIM];
-  __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];   // per-warp broadcast slot (curve output)
-  __shared__ double s_data[MODE == kModeCurves ? 1 : kDataSmemDoubles];
-  DataView dv = a.dv;
-  if (MODE != kModeCurves) stage_data(a.dv, dv, s_data, BLOCK);       // (stage_theta's barrier covers it)
-  const int lpw = (MODE == kModeCurves && a.lanes_per_walker > 1) ? a.lanes_per_walker : 1;
-  stage_theta<BLOCK>(a.theta, a.W, a.ndim, s_theta, a.order, lpw);
-  const int slot = blockIdx.x * BLOCK + threadIdx.x;
-  const int i = slot / lpw;
-  const bool have = (i < a.W) && (slot % lpw == 0);
-  const int w = (a.order && have) ? a.order[i] : i;
-  void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
-  // (a deferred walker claims its queue slot -- and leaves its hand-over record there -- inside evaluate_walker)
-  ResumeSink sink{(MODE != kModeCurves && a.resume) ? a.queue_count : nullptr, a.resume, -1};
-  if (eval_one<MODE, BLOCK, false>(a, dv, have, w, s_theta + threadIdx.x * a.ndim, s_buf, scratch, &sink))
-    a.queue[sink.count ? sink.slot : atomicAdd(a.queue_count, 1)] = w;
-}
-
-// Second launch: the walkers bucketed as stiff, with the implicit integrator available.
-#ifndef MP_STIFF_MIN_WARPS
-#define MP_STIFF_MIN_WARPS 12     // resident warps per SM the implicit variant is compiled for
-#endif
-template <int MODE, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) eval_stiff_kernel(const __grid_constant__ KernelArgs a) {
-  __shared__ double s_buf[NodeBuf<MODE>::n * BLOCK];
-  __shared__ Walker s_walker[MODE == kModeCurves ? BLOCK / 32 : 1];
-  void* scratch = &s_walker[MODE == kModeCurves ? (threadIdx.x >> 5) : 0];
-  // One batch per block and a grid sized for the whole launch (the queue length is only known on the
-  // device): blocks beyond the queue exit at once, and the hardware block scheduler balances the
-  // very unequal walkers of this bucket.
-  const int n = *a.queue_count;
-  const int i = blockIdx.x * BLOCK + threadIdx.x;
-  if (blockIdx.x * BLOCK >= n) return;
-  const bool have = i < n;
-  const int w = have ? a.queue[i] : 0;
-  double th[MP_MAX_NDIM];
-  for (int d = 0; d < a.ndim; ++d) th[d] = a.theta[(size_t)w * a.ndim + d];
-  eval_one<MODE, BLOCK, true>(a, a.dv, have, w, th, s_buf, scratch, nullptr,
-                              (MODE != kModeCurves && a.resume && have) ? a.resume + (size_t)i * kResumeLen : nullptr);
-}
-
-struct StretchArgs {
-  KernelArgs k;          // k.theta unused; k.lnp unused
+// The stretch move wrapped around an evaluation (mp_stretch_half_step / mp_ensemble_half_step):
+//   z = ((a-1) u + 1)^2 / a ; q = c - (c - s) z ; accept iff (ndim-1) ln z + lp(q) - lp(s) > ln u'
+// (Goodman & Weare 2010; emcee's RedBlueMove).  setup_kernel forms the proposals, the reduce kernels accept.
+struct Move {
   double* coords;        // [nwalkers][ndim], updated in place
   double* lnp;           // [nwalkers]
   // who moves against whom: explicit index lists (mp_stretch_half_step) ...
@@ -211,11 +69,13 @@ struct StretchArgs {
   // partner is drawn from P(cpos0 + [0, n_complement))
   SplitPerm perm;
   int pos0, cpos0;
-  int n_active, n_complement;
+  int n_complement;
   double a;
   uint64_t seed, step;   // step: the half-step counter (RNG counter word)
+  double* prop;          // [n_active][ndim] the proposals (work space)
   int* accepted;         // [nwalkers] counters (may be null)
   int* status;           // [nwalkers] MP_WALKER_* bits of the latest proposal (may be null)
+  int* n_rhs;            // [nwalkers] (may be null)
   // replicas of (coords, lnp) on the other ranks, peer-mapped over NVLink: accepted rows are stored there too
   int n_peers;
   double* peer_coords[MP_MAX_PEERS];
@@ -226,110 +86,393 @@ struct StretchArgs {
   int bad_capacity;
 };
 
-// One emcee StretchMove half-step (Goodman & Weare 2010; emcee RedBlueMove):
-//   z = ((a-1) u + 1)^2 / a ; q = c - (c - s) z ; accept iff (ndim-1) ln z + lp(q) - lp(s) > ln u'
-// fused with the likelihood so a half-step is one launch (plus the stiff-bucket launch, which
-// finds an empty queue for ensembles near the synthetic truths).  `i` is the mover's index in this
-// launch.  Returns true when deferred.
-template <int BLOCK, bool STIFF>
-__device__ __forceinline__ bool stretch_one(const StretchArgs& s, bool have, int i, double* s_buf, ResumeSink* sink = nullptr,
-                                            const double* rec_in = nullptr) {
-  const KernelArgs& a = s.k;
-  const int ndim = a.ndim;
-  const int me = s.active ? s.active[i] : (int)perm_at(s.perm, (uint32_t)(s.pos0 + i));
-  // counter = (half-step, walker); two Philox blocks give u_z, u_partner, u_accept
-  const Philox r0 = philox4x32_10((uint32_t)s.step, (uint32_t)(s.step >> 32), (uint32_t)me, 0u,
-                                  (uint32_t)s.seed, (uint32_t)(s.seed >> 32));
-  const Philox r1 = philox4x32_10((uint32_t)s.step, (uint32_t)(s.step >> 32), (uint32_t)me, 1u,
-                                  (uint32_t)s.seed, (uint32_t)(s.seed >> 32));
+struct Draw {
+  double z, ua;
+  int me, partner;
+};
+// counter = (half-step, walker); two Philox blocks give u_z, u_partner, u_accept
+__device__ __forceinline__ Draw draw_for(const Move& m, int i) {
+  Draw d;
+  d.me = m.active ? m.active[i] : (int)perm_at(m.perm, (uint32_t)(m.pos0 + i));
+  const Philox r0 = philox4x32_10((uint32_t)m.step, (uint32_t)(m.step >> 32), (uint32_t)d.me, 0u,
+                                  (uint32_t)m.seed, (uint32_t)(m.seed >> 32));
+  const Philox r1 = philox4x32_10((uint32_t)m.step, (uint32_t)(m.step >> 32), (uint32_t)d.me, 1u,
+                                  (uint32_t)m.seed, (uint32_t)(m.seed >> 32));
   const double uz = u01(r0.c[0], r0.c[1]);
   const double up = u01(r0.c[2], r0.c[3]);
-  const double ua = u01(r1.c[0], r1.c[1]);
-  const double zr = __dadd_rn(__dmul_rn(s.a - 1.0, uz), 1.0);
-  const double z = __ddiv_rn(__dmul_rn(zr, zr), s.a);
-  int pj = (int)(up * s.n_complement);
-  if (pj >= s.n_complement) pj = s.n_complement - 1;
-  const int partner = s.complement ? s.complement[pj] : (int)perm_at(s.perm, (uint32_t)(s.cpos0 + pj));
-  double q[MP_MAX_NDIM];
-  for (int d = 0; d < ndim; ++d) {
-    const double c = s.coords[(size_t)partner * ndim + d];
-    const double x = s.coords[(size_t)me * ndim + d];
-    q[d] = __dadd_rn(c, -__dmul_rn(__dadd_rn(c, -x), z));   // no FMA contraction: reproducible on the host
-  }
-  int st = kWalkerOk, nr = 0;
-  double lp_new = -INFINITY;
-  const bool live = have && (!a.prior_enabled || prior_accepts(q, ndim, a.lower, a.upper));
-  if (have && !live) st = kWalkerPriorReject;
-  {
-    double pars[6], dipeff, propeff, f_beam;
-    unpack_theta(a.sp, q, ndim, pars, dipeff, propeff, f_beam);
-    Walker wk;
-    walker_setup(a.sp, pars, dipeff, propeff, f_beam, a.dv.t_start, wk);
-    const double chi2 = evaluate_walker<kModeLnprob, kNB, STIFF>(a.sp, a.dv, wk, live, s_buf + threadIdx.x, BLOCK,
-                                                                 st, nr, nullptr, nullptr, 1, nullptr, nullptr, sink, rec_in);
-    if (!STIFF && (st & kWalkerDeferred)) return true;
-    if (live) {
-      double ll = -0.5 * chi2;
-      if (st & kWalkerIntegratorFail) {
-        ll = -INFINITY;
-      } else if (!isfinite(ll)) {
-        st |= kWalkerNonfiniteLnlike;
-        ll = -INFINITY;
+  d.ua = u01(r1.c[0], r1.c[1]);
+  const double zr = __dadd_rn(__dmul_rn(m.a - 1.0, uz), 1.0);
+  d.z = __ddiv_rn(__dmul_rn(zr, zr), m.a);
+  int pj = (int)(up * m.n_complement);
+  if (pj >= m.n_complement) pj = m.n_complement - 1;
+  d.partner = m.complement ? m.complement[pj] : (int)perm_at(m.perm, (uint32_t)(m.cpos0 + pj));
+  return d;
+}
+
+constexpr int kRecWords = (int)(sizeof(WalkerRec) / 8);
+static_assert(sizeof(WalkerRec) % 8 == 0, "WalkerRec is moved as 8-byte words");
+__device__ __forceinline__ void rec_store(const Work& k, int i, const WalkerRec& r) {
+  unsigned long long tmp[kRecWords];
+  memcpy(tmp, &r, sizeof(r));
+#pragma unroll
+  for (int c = 0; c < kRecWords; ++c) k.recs[(size_t)c * k.stride + i] = tmp[c];
+}
+__device__ __forceinline__ void rec_load(const Work& k, int i, WalkerRec& r) {
+  unsigned long long tmp[kRecWords];
+#pragma unroll
+  for (int c = 0; c < kRecWords; ++c) tmp[c] = k.recs[(size_t)c * k.stride + i];
+  memcpy(&r, tmp, sizeof(r));
+}
+
+// Only what stage 3 reads of a record (disc_mass and the luminosity stage: 19 of its 55 words).
+#define MP_WFIELD(name) \
+  w.name = __longlong_as_double((long long)k.recs[((offsetof(WalkerRec, w) + offsetof(Walker, name)) / 8) * (size_t)k.stride + i])
+__device__ __forceinline__ void rec_load_lum(const Work& k, int i, Walker& w) {
+  MP_WFIELD(inv_tv); MP_WFIELD(eps); MP_WFIELD(u0); MP_WFIELD(K); MP_WFIELD(C); MP_WFIELD(M_init); MP_WFIELD(u_late);
+  MP_WFIELD(l_inv_tv); MP_WFIELD(l_Ccap); MP_WFIELD(l_kc); MP_WFIELD(l_sqrtA); MP_WFIELD(l_sGMkc); MP_WFIELD(l_GM_kc);
+  MP_WFIELD(Ldip_coef); MP_WFIELD(dipeff); MP_WFIELD(propeff); MP_WFIELD(f_beam); MP_WFIELD(omega0);
+  w.bad = (int)k.recs[((offsetof(WalkerRec, w) + offsetof(Walker, bad)) / 8) * (size_t)k.stride + i];
+}
+#undef MP_WFIELD
+
+// Warp-aggregated append: the lanes with `want` get consecutive slots of a list whose length is *count.
+__device__ __forceinline__ int warp_append(bool want, int* count) {
+  const unsigned m = __ballot_sync(kFull, want);
+  if (!m) return -1;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(kFull, base, leader);
+  return want ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// ---- stage 1: setup ---------------------------------------------------------------------------------
+// MOVE = false: walker i's parameters are theta[i][:].  MOVE = true: walker i is mover i of a stretch-move
+// half-step and its parameters are the proposal q, formed here and kept in m.prop for the accept step.
+template <bool MOVE>
+__global__ void __launch_bounds__(128, 4) setup_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k,
+                                                    const double* __restrict__ theta, const __grid_constant__ Move m) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool have = i < k.W;
+  const int ndim = p.ndim;
+  double th[MP_MAX_NDIM];
+  if (have) {
+    if (MOVE) {
+      const Draw d = draw_for(m, i);
+      for (int c = 0; c < ndim; ++c) {
+        const double cc = m.coords[(size_t)d.partner * ndim + c];
+        const double x = m.coords[(size_t)d.me * ndim + c];
+        th[c] = __dadd_rn(cc, -__dmul_rn(__dadd_rn(cc, -x), d.z));   // no FMA contraction: reproducible on the host
+        m.prop[(size_t)i * ndim + c] = th[c];
       }
-      lp_new = ll;
+    } else {
+      for (int c = 0; c < ndim; ++c) th[c] = theta[(size_t)i * ndim + c];
     }
   }
-  if (!have) return false;
-  const double lp_old = s.lnp[me];
-  const double lnpdiff = __dadd_rn(__dadd_rn(__dmul_rn(ndim - 1.0, log(z)), lp_new), -lp_old);
-  const bool accept = lnpdiff > log(ua);
+  bool to_explicit = false, to_implicit = false;
+  double y0 = 0.0, h0 = 0.0;
+  int n_rhs0 = 0;
+  if (have) {
+    WalkerRec r;
+    const double t_end = p.dv.n_nodes > 0 ? p.dv.node_t[p.dv.n_nodes - 1] : p.dv.t_start;
+    prepare_walker(p.sp, th, ndim, p.prior_enabled != 0, p.lower, p.upper, p.dv.t_start, t_end, r);
+    if (!(r.status & kWalkerPriorReject)) rec_store(k, i, r);
+    y0 = r.y0; h0 = r.h0; n_rhs0 = r.n_rhs;
+    k.status[i] = r.status;
+    k.n_rhs[i] = r.n_rhs;
+    // (a walker whose initialisation failed still goes to the integrator, which marks its nodes)
+    const bool go = (r.status == kWalkerOk || r.status == kWalkerIntegratorFail) && p.dv.n_nodes > 0;
+    to_implicit = go && p.sp.bucciantini && r.status == kWalkerOk;
+    to_explicit = go && !to_implicit;
+  }
+  const int we = warp_append(to_explicit, k.counters + 0);
+  if (to_explicit) k.work[we] = i;
+  const int wi = warp_append(to_implicit, k.counters + 2);
+  if (to_implicit) {
+    StiffRec q;
+    q.t = p.dv.t_start; q.y = y0; q.h = h0; q.wid = i; q.jn = 0; q.n_rhs = n_rhs0; q.n_steps = 0;
+    k.squeue[wi] = q;
+  }
+}
+
+// ---- stage 2: advance -------------------------------------------------------------------------------
+// Persistent warps.  Every trip of the loop is ONE integrator step for every lane that holds a walker; a lane
+// whose walker is finished (all nodes delivered), failed or -- explicit variant -- turned stiff hands it on
+// and takes the next walker off the queue at the top of the next trip, so the lanes of a warp stay busy
+// whatever the spread of step counts in the ensemble (40 .. 10^3 over the prior box).  The cheap, divergent
+// parts (delivering nodes, hand-over, taking a walker) sit between the steps.
+#ifndef MP_MIN_BLOCKS_32
+#define MP_MIN_BLOCKS_32 16
+#endif
+#ifndef MP_MIN_BLOCKS_64
+#define MP_MIN_BLOCKS_64 8
+#endif
+#ifndef MP_STIFF_MIN_WARPS
+#define MP_STIFF_MIN_WARPS 12     // resident warps per SM the implicit variant is compiled for
+#endif
+constexpr int kNodeSmemDoubles = 512;      // node times staged per block when they fit (4 KB)
+
+template <bool STIFF, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, STIFF ? (MP_STIFF_MIN_WARPS * 32 / BLOCK) : (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64))
+advance_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k) {
+  __shared__ double s_nodes[kNodeSmemDoubles];
+  const int Nn = p.dv.n_nodes;
+  const double* node_t = p.dv.node_t;
+  if (Nn <= kNodeSmemDoubles) {
+    for (int j = threadIdx.x; j < Nn; j += BLOCK) s_nodes[j] = node_t[j];
+    node_t = s_nodes;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31;
+  const int n_items = k.counters[STIFF ? 2 : 0];
+  int* next = k.counters + (STIFF ? 3 : 1);
+  const double t_end = ldd(node_t + (Nn - 1));
+  Walker w;
+  Integrator in;
+  in.status = kWalkerOk; in.stiff = 0; in.n_rhs = 0; in.t = p.dv.t_start;
+  int wid = 0, jn = 0;
+  double* row = k.ybuf;
+  bool have = false, empty = false;
+  for (;;) {
+    // ---- take walkers
+    const unsigned idle = __ballot_sync(kFull, !have);
+    if (idle && !empty) {
+      const int leader = __ffs(idle) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(next, __popc(idle));
+      base = __shfl_sync(kFull, base, leader);
+      if (base + __popc(idle) >= n_items) empty = true;          // (uniform across the warp)
+      const int my = base + __popc(idle & ((1u << lane) - 1u));
+      if (!have && my < n_items) {
+        have = true;
+        WalkerRec r;
+        if (STIFF) {
+          const StiffRec q = k.squeue[my];
+          wid = q.wid;
+          rec_load(k, wid, r);
+          integrator_load_stiff(q, in);
+          jn = q.jn;
+        } else {
+          wid = k.work[my];
+          rec_load(k, wid, r);
+          integrator_load(r, p.dv.t_start, in);
+          if (r.status != kWalkerOk) in.status = kWalkerIntegratorFail;
+          jn = 0;
+        }
+        w = r.w;
+        row = k.ybuf + (size_t)wid * k.ws;
+        jn = drain_nodes<STIFF>(in, jn, Nn, node_t, row, k.ns);      // a node at the starting time
+      }
+    }
+    if (!__any_sync(kFull, have)) break;
+    // ---- one step for every lane that holds a walker (a fresh walker whose nodes are all delivered
+    // already, or whose initialisation failed, skips it)
+    if (have && jn < Nn && in.status == kWalkerOk) {
+      if (STIFF) radau_step(p.sp, w, t_end, in);
+      else integrator_step(p.sp, w, t_end, in);
+      jn = drain_nodes<STIFF>(in, jn, Nn, node_t, row, k.ns);
+    }
+    // ---- hand finished walkers on
+    if (have) {
+      const bool failed = in.status != kWalkerOk;
+      const bool stiff = !STIFF && in.stiff && !failed && jn < Nn;
+      if (jn >= Nn || failed || stiff) {
+        if (failed)
+          for (; jn < Nn; ++jn) row[jn * k.ns] = NAN;            // stage 3 sees no solution there
+        if (stiff) {
+          // (explicit variant) the implicit integrator picks the walker up where this one stopped
+          StiffRec q;
+          q.t = in.t; q.y = in.omega; q.h = in.h; q.wid = wid; q.jn = jn; q.n_rhs = in.n_rhs; q.n_steps = in.n_steps;
+          k.squeue[atomicAdd(k.counters + 2, 1)] = q;
+        } else {
+          k.status[wid] |= in.status;
+          k.n_rhs[wid] = in.n_rhs;
+        }
+        have = false;
+      }
+    }
+  }
+}
+
+// ---- stage 3: reduce ----------------------------------------------------------------------------------
+// The dataset a block works against -- node times and, per datum, y/yerr, 1e-50/yerr, x - t_lo, the
+// interpolation weight and the lower-node index -- staged in shared memory when it fits the budget below
+// (the synthetic datasets take 2.2 KB).
+constexpr int kDataSmemDoubles = 768;      // 6 KB per block
+__device__ __forceinline__ bool stage_data(const DataView& g, DataView& s, double* buf, int nthreads) {
+  const int Nn = g.n_nodes, D = g.n_data;
+  const int need = Nn + 4 * D + (D + 1) / 2;
+  if (need > kDataSmemDoubles) return false;
+  double* q = buf;
+  double* nt = q; q += Nn;
+  double* ys = q; q += D;
+  double* c = q; q += D;
+  double* dx = q; q += D;
+  double* w = q; q += D;
+  int* lo = reinterpret_cast<int*>(q);
+  for (int i = threadIdx.x; i < Nn; i += nthreads) nt[i] = g.node_t[i];
+  for (int i = threadIdx.x; i < D; i += nthreads) {
+    ys[i] = g.dat_ys[i]; c[i] = g.dat_c[i]; dx[i] = g.dat_dx[i]; w[i] = g.dat_w[i]; lo[i] = g.dat_lo[i];
+  }
+  s = g;
+  s.node_t = nt; s.dat_ys = ys; s.dat_c = c; s.dat_dx = dx; s.dat_w = w; s.dat_lo = lo;
+  __syncthreads();
+  return true;
+}
+
+// Where a finished evaluation goes: the caller's arrays, or the accept step of the stretch move.
+struct Sink {
+  double* lnp;     // [W]
+  int* status;     // [W] or null
+  int* n_rhs;      // [W] or null
+};
+
+template <bool MOVE>
+__device__ __forceinline__ void deliver(const Problem& p, const Work& k, const Sink& s, const Move& m, int i, double lp_new,
+                                        int st) {
+  const int nr = k.n_rhs[i];
+  if (!MOVE) {
+    s.lnp[i] = lp_new;
+    if (s.status) s.status[i] = st;
+    if (s.n_rhs) s.n_rhs[i] = nr;
+    return;
+  }
+  const int ndim = p.ndim;
+  const Draw d = draw_for(m, i);
+  const int me = d.me;
+  const double* q = m.prop + (size_t)i * ndim;
+  const double lp_old = m.lnp[me];
+  const double lnpdiff = __dadd_rn(__dadd_rn(__dmul_rn(ndim - 1.0, log(d.z)), lp_new), -lp_old);
+  const bool accept = lnpdiff > log(d.ua);
   if (accept) {
-    for (int d = 0; d < ndim; ++d) s.coords[(size_t)me * ndim + d] = q[d];
-    s.lnp[me] = lp_new;
+    for (int c = 0; c < ndim; ++c) m.coords[(size_t)me * ndim + c] = q[c];
+    m.lnp[me] = lp_new;
     // the same row into every other rank's replica (NVLink peer stores; the caller's mp_peer_barrier
     // makes them visible before the next half-step reads them)
-    for (int p = 0; p < s.n_peers; ++p) {
-      double* pc = s.peer_coords[p] + (size_t)me * ndim;
-      for (int d = 0; d < ndim; ++d) pc[d] = q[d];
-      s.peer_lnp[p][me] = lp_new;
+    for (int r = 0; r < m.n_peers; ++r) {
+      double* pc = m.peer_coords[r] + (size_t)me * ndim;
+      for (int c = 0; c < ndim; ++c) pc[c] = q[c];
+      m.peer_lnp[r][me] = lp_new;
     }
-    if (s.accepted) s.accepted[me] += 1;
+    if (m.accepted) m.accepted[me] += 1;
   }
-  if (s.pack_out) {
-    double* row = s.pack_out + (size_t)i * (ndim + 1);
-    for (int d = 0; d < ndim; ++d) row[d] = accept ? q[d] : s.coords[(size_t)me * ndim + d];
-    row[ndim] = accept ? lp_new : lp_old;
+  if (m.pack_out) {
+    double* rowp = m.pack_out + (size_t)i * (ndim + 1);
+    for (int c = 0; c < ndim; ++c) rowp[c] = accept ? q[c] : m.coords[(size_t)me * ndim + c];
+    rowp[ndim] = accept ? lp_new : lp_old;
   }
-  if (s.status) s.status[me] = st;
-  if (s.bad_count && (st & (kWalkerIntegratorFail | kWalkerNonfiniteLnlike))) {
-    const int slot = atomicAdd(s.bad_count, 1);
-    if (slot < s.bad_capacity)
-      for (int d = 0; d < ndim; ++d) s.bad_rows[(size_t)slot * ndim + d] = q[d];
+  if (m.status) m.status[me] = st;
+  if (m.bad_count && (st & (kWalkerIntegratorFail | kWalkerNonfiniteLnlike))) {
+    const int slot = atomicAdd(m.bad_count, 1);
+    if (slot < m.bad_capacity)
+      for (int c = 0; c < ndim; ++c) m.bad_rows[(size_t)slot * ndim + c] = q[c];
   }
-  if (a.n_rhs) a.n_rhs[me] = nr;
-  return false;
+  if (m.n_rhs) m.n_rhs[me] = nr;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64))
-stretch_kernel(const __grid_constant__ StretchArgs s) {
-  __shared__ double s_buf[kNB * BLOCK];
-  const int i = blockIdx.x * BLOCK + threadIdx.x;
-  const bool have = i < s.n_active;
-  ResumeSink sink{s.k.resume ? s.k.queue_count : nullptr, s.k.resume, -1};
-  if (stretch_one<BLOCK, false>(s, have, have ? i : 0, s_buf, &sink))
-    s.k.queue[sink.count ? sink.slot : atomicAdd(s.k.queue_count, 1)] = i;
+// One thread per walker, nodes one after the other: every lane of a warp walks the same node and datum
+// indices (the dataset is shared), so the loop is converged.  Used when the dataset is small (synthetic
+// light curves: 50 points) -- there a warp per walker would leave half its lanes without a node.
+template <int MODE, bool MOVE>
+__global__ void __launch_bounds__(64, 12) reduce_rows_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k,
+                                                         const __grid_constant__ Sink s, double* __restrict__ out,
+                                                         const __grid_constant__ Move m) {
+  __shared__ double s_data[kDataSmemDoubles];
+  DataView dv = p.dv;
+  stage_data(p.dv, dv, s_data, 64);
+  const int i = blockIdx.x * 64 + threadIdx.x;
+  if (i >= k.W) return;
+  int st = k.status[i];
+  double result = -INFINITY;
+  if (!(st & kWalkerPriorReject)) {
+    Walker w;
+    rec_load_lum(k, i, w);
+    double* o = (MODE == kModeModelAtData) ? out + (size_t)i * dv.n_data : nullptr;
+    const double chi2 = reduce_rows<MODE>(p.sp, dv, w, k.ybuf + (size_t)i * k.ws, o, nullptr, 1, p.dat_orig, k.ns);
+    if (MODE == kModeLnprob) result = lnlike_of(chi2, st);                       // + lnprior == 0.0
+  }
+  if (MODE == kModeLnprob) deliver<MOVE>(p, k, s, m, i, result, st);
+  else if (s.status) s.status[i] = st;
 }
 
-template <int BLOCK>
-__global__ void __launch_bounds__(BLOCK, MP_STIFF_MIN_WARPS * 32 / BLOCK) stretch_stiff_kernel(const __grid_constant__ StretchArgs s) {
-  __shared__ double s_buf[kNB * BLOCK];
-  const int n = *s.k.queue_count;
-  const int i = blockIdx.x * BLOCK + threadIdx.x;
-  if (blockIdx.x * BLOCK >= n) return;
-  const bool have = i < n;
-  stretch_one<BLOCK, true>(s, have, have ? s.k.queue[i] : 0, s_buf, nullptr,
-                           (s.k.resume && have) ? s.k.resume + (size_t)i * kResumeLen : nullptr);
+// One warp per walker, one DATUM per lane: the lane evaluates the luminosity stage at its datum's two
+// bracketing nodes (one if the datum sits on a node), interpolates, forms its residual -- and the chi-square
+// is a warp-shuffle reduction over the data.  Used for the large datasets (the short-GRB sample: up to 1944
+// points, ~2 nodes per datum), and it is what makes a small ensemble on such a burst run at the speed of the
+// integration alone instead of one thread walking thousands of nodes.
+template <int MODE, bool MOVE>
+__global__ void __launch_bounds__(128) reduce_coop_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k,
+                                                          const __grid_constant__ Sink s, double* __restrict__ out,
+                                                          const __grid_constant__ Move m) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * 128 + threadIdx.x) >> 5;
+  if (i >= k.W) return;
+  int st = k.status[i];
+  double chi2 = 0.0;
+  if (!(st & kWalkerPriorReject)) {
+    Walker w;
+    rec_load_lum(k, i, w);                                     // (every lane the same words: broadcast loads)
+    const double* row = k.ybuf + (size_t)i * k.ws;             // node-minor: k.ns == 1
+    const DataView& dv = p.dv;
+    for (int d0 = 0; d0 < dv.n_data; d0 += 32) {
+      const int d = d0 + lane;
+      if (d < dv.n_data) {
+        const int lo = dv.dat_lo[d];
+        const double dx = dv.dat_dx[d];
+        double M, om;
+        const double L_lo = node_luminosity(p.sp, w, dv.node_t[lo], dv.t_start, row[lo], false, M, om).tot;
+        double mod = L_lo;                                     // datum sits on a grid node
+        if (dx != 0.0) {
+          const double L_hi = node_luminosity(p.sp, w, dv.node_t[lo + 1], dv.t_start, row[lo + 1], false, M, om).tot;
+          mod = fma(L_hi - L_lo, dv.dat_w[d], L_lo);           // np.interp: slope*(x-x_lo)+y_lo
+        }
+        if (MODE == kModeLnprob) {
+          const double r = fma(-mod, dv.dat_c[d], dv.dat_ys[d]);   // (y - mod/1e50)/yerr
+          chi2 = fma(r, r, chi2);
+        } else {
+          out[(size_t)i * dv.n_data + (p.dat_orig ? p.dat_orig[d] : d)] = mod * 1.0e-50;
+        }
+      }
+    }
+    if (MODE == kModeLnprob)
+      for (int off = 16; off > 0; off >>= 1) chi2 += __shfl_xor_sync(kFull, chi2, off);   // same value on every lane
+  }
+  if (lane != 0) return;
+  if (MODE == kModeLnprob) {
+    double result = -INFINITY;
+    if (!(st & kWalkerPriorReject)) result = lnlike_of(chi2, st);
+    deliver<MOVE>(p, k, s, m, i, result, st);
+  } else if (s.status) {
+    s.status[i] = st;
+  }
+}
+
+// Light curves: one warp per walker, one NODE per lane, so the three output rows (and the state rows) are
+// written as 256-byte runs along the node axis.  out [W][3][Nn] = Ltot, Lprop, Ldip (/1e50); state [W][2][Nn].
+__global__ void __launch_bounds__(128) reduce_curves_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k,
+                                                            double* __restrict__ out, double* __restrict__ state,
+                                                            int* __restrict__ status) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * 128 + threadIdx.x) >> 5;
+  if (i >= k.W) return;
+  Walker w;
+  rec_load_lum(k, i, w);
+  const int Nn = p.dv.n_nodes;
+  const double* row = k.ybuf + (size_t)i * k.ws;               // node-minor: k.ns == 1
+  double* o = out + (size_t)i * 3 * Nn;
+  double* so = state ? state + (size_t)i * 2 * Nn : nullptr;
+  for (int j = lane; j < Nn; j += 32) {
+    double M, om;
+    const Lum L = node_luminosity(p.sp, w, p.dv.node_t[j], p.dv.t_start, row[j], so != nullptr, M, om);
+    o[j] = L.tot * 1.0e-50;            // (/1e50, funcs.py:231,236, as one multiplication: <= 1 ulp)
+    o[Nn + j] = L.prop * 1.0e-50;
+    o[2 * Nn + j] = L.dip * 1.0e-50;
+    if (so) {
+      so[j] = M;
+      so[Nn + j] = om;
+    }
+  }
+  if (lane == 0 && status) status[i] = k.status[i];
 }
 
 // Scatter of all-gathered packs (the collective exchange): packed row i of the half -> walker P(pos0 + i).
@@ -478,31 +621,26 @@ struct mp_handle {
   double *s_theta = nullptr, *s_out = nullptr, *s_state = nullptr, *s_lnp = nullptr;
   int *s_status = nullptr, *s_nrhs = nullptr, *s_cstatus = nullptr;
   size_t cap_theta = 0, cap_out = 0, cap_state = 0, cap_w = 0, cap_cstatus = 0;
-  // Two pipeline lanes: each has its own stream and its own stiff-walker queue, so that the
-  // host-pointer entry points can overlap the H2D copy of one chunk with the kernel of the previous
-  // one.  Device-pointer entry points use lane 0's queue on the caller's stream.
+  // A lane = a stream plus the work space the stages of a launch hand to one another.  The handle owns two
+  // pipeline lanes so that the host-pointer entry points can overlap the H2D copy of one chunk with the
+  // kernels of the previous one.  Device-pointer entry points run on the caller's stream, and every such
+  // stream gets a lane of its own (work space only): calls on one handle from different streams -- several
+  // ensembles on one dataset, a device call next to an mp_lnprob_batch_async in flight -- never share work
+  // space; calls on ONE stream are ordered by the stream.
   struct Lane {
     cudaStream_t stream = nullptr;
-    int* queue = nullptr;        // walkers deferred to the stiff launch
-    int* queue_count = nullptr;
-    size_t cap_queue = 0;
-    double* resume = nullptr;    // hand-over records, one per queue slot
-    size_t cap_resume = 0;
-    // walker bucketing (mp_set_bucketing): sort keys / walker ids (double-buffered) and CUB's scratch
-    unsigned *key_in = nullptr, *key_out = nullptr;
-    int *id_in = nullptr, *id_out = nullptr;
-    void* sort_tmp = nullptr;
-    size_t cap_sort = 0, cap_tmp = 0;
+    unsigned long long* recs = nullptr;
+    double* ybuf = nullptr;
+    int *status = nullptr, *n_rhs = nullptr, *work = nullptr, *counters = nullptr;
+    StiffRec* squeue = nullptr;
+    double* prop = nullptr;
+    size_t cap_walkers = 0, cap_ybuf = 0, cap_prop = 0;
   } lanes[2];
-  // Device-pointer entry points run on the caller's stream.  Each stream gets its own queue set, so calls
-  // on one handle from different streams (several ensembles on one dataset, a device call next to an
-  // mp_lnprob_batch_async in flight) never share a stiff queue; calls on ONE stream are ordered by the stream.
   std::map<cudaStream_t, Lane> user_lanes;
   std::mutex user_lanes_mu;
-  int bucketing = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;   // == lanes[0].stream
-  Lane* last_lane = nullptr;       // queue set of the most recent device-pointer launch (mp_last_stiff_count)
+  Lane* last_lane = nullptr;       // work space of the most recent launch (mp_last_stiff_count)
 };
 
 template <typename T>
@@ -514,6 +652,8 @@ static int upload(T** dst, const std::vector<T>& v) {
   return MP_OK;
 }
 
+// Grow-only device buffer.  (cudaFree waits for the device, so a buffer an earlier launch still uses is
+// released only after that launch has finished.)
 template <typename T>
 static int ensure(T** p, size_t* cap, size_t need) {
   if (need <= *cap) return MP_OK;
@@ -564,11 +704,9 @@ extern "C" int mp_create(const mp_model_spec* spec, const mp_prior_spec* prior, 
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
   }
   for (auto& L : h->lanes) {
-    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMalloc((void**)&L.queue_count, sizeof(int)) != cudaSuccess ||
-        cudaMemset(L.queue_count, 0, sizeof(int)) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) {
       mp_destroy(h);
-      return fail(MP_ERR_CUDA, "mp_create: stream / queue allocation failed");
+      return fail(MP_ERR_CUDA, "mp_create: stream creation failed");
     }
   }
   h->stream = h->lanes[0].stream;
@@ -589,6 +727,7 @@ extern "C" int mp_create(const mp_model_spec* spec, const mp_prior_spec* prior, 
 extern "C" void mp_destroy(mp_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
   cudaFree(h->data_nodes.node_t);
   cudaFree(h->d_y); cudaFree(h->d_yerr); cudaFree(h->d_dx); cudaFree(h->d_Dx);
   cudaFree(h->d_lo); cudaFree(h->d_orig);
@@ -596,8 +735,8 @@ extern "C" void mp_destroy(mp_handle* h) {
   cudaFree(h->s_theta); cudaFree(h->s_out); cudaFree(h->s_state); cudaFree(h->s_lnp);
   cudaFree(h->s_status); cudaFree(h->s_nrhs); cudaFree(h->s_cstatus);
   auto free_lane = [](mp_handle::Lane& L) {
-    cudaFree(L.queue); cudaFree(L.queue_count); cudaFree(L.resume);
-    cudaFree(L.key_in); cudaFree(L.key_out); cudaFree(L.id_in); cudaFree(L.id_out); cudaFree(L.sort_tmp);
+    cudaFree(L.recs); cudaFree(L.ybuf); cudaFree(L.status); cudaFree(L.n_rhs); cudaFree(L.work);
+    cudaFree(L.counters); cudaFree(L.squeue); cudaFree(L.prop);
     if (L.stream) cudaStreamDestroy(L.stream);
   };
   for (auto& L : h->lanes) free_lane(L);
@@ -611,173 +750,134 @@ extern "C" int mp_set_prior(mp_handle* h, const mp_prior_spec* prior) {
   return MP_OK;
 }
 
-extern "C" int mp_set_bucketing(mp_handle* h, int32_t enabled) {
-  if (!h) return fail(MP_ERR_BAD_ARG, "mp_set_bucketing: null handle");
-  h->bucketing = enabled ? 1 : 0;
-  return MP_OK;
-}
-
-static int fill_args(mp_handle* h, KernelArgs& a, const DeviceNodes& nodes, bool with_data, int ndim, int W,
-                     bool use_prior) {
+static int fill_problem(mp_handle* h, Problem& p, const DeviceNodes& nodes, bool with_data, int ndim, int W,
+                        bool use_prior) {
   if (ndim < 6 || ndim > MP_MAX_NDIM) return fail(MP_ERR_BAD_ARG, "ndim must be 6, 7, 8 or 9");
   if (W < 0) return fail(MP_ERR_BAD_ARG, "negative walker count");
   if (use_prior && h->prior.enabled && h->prior.ndim != ndim)
     return fail(MP_ERR_BAD_ARG, "prior dimension does not match ndim");
-  std::memset(&a, 0, sizeof(a));
-  a.sp = h->spec;
-  a.dv.n_nodes = nodes.n_nodes;
-  a.dv.node_t = nodes.node_t;
-  a.dv.t_start = h->grid[0];
+  std::memset(&p, 0, sizeof(p));
+  p.sp = h->spec;
+  p.dv.n_nodes = nodes.n_nodes;
+  p.dv.node_t = nodes.node_t;
+  p.dv.t_start = h->grid[0];
   if (with_data) {
-    a.dv.n_data = h->D;
-    a.dv.dat_ys = h->d_y;
-    a.dv.dat_c = h->d_yerr;
-    a.dv.dat_dx = h->d_dx;
-    a.dv.dat_w = h->d_Dx;
-    a.dv.dat_lo = h->d_lo;
-    a.dat_orig = h->d_orig;
+    p.dv.n_data = h->D;
+    p.dv.dat_ys = h->d_y;
+    p.dv.dat_c = h->d_yerr;
+    p.dv.dat_dx = h->d_dx;
+    p.dv.dat_w = h->d_Dx;
+    p.dv.dat_lo = h->d_lo;
+    p.dat_orig = h->d_orig;
   }
-  a.prior_enabled = use_prior ? h->prior.enabled : 0;
+  p.prior_enabled = use_prior ? h->prior.enabled : 0;
   for (int i = 0; i < MP_MAX_NDIM; ++i) {
-    a.lower[i] = h->prior.lower[i];
-    a.upper[i] = h->prior.upper[i];
+    p.lower[i] = h->prior.lower[i];
+    p.upper[i] = h->prior.upper[i];
   }
-  a.ndim = ndim;
-  a.W = W;
+  p.ndim = ndim;
   return MP_OK;
 }
 
-// lane >= 0: one of the handle's own pipeline lanes; lane < 0: the queue set of the caller's stream
+// lane >= 0: one of the handle's own pipeline lanes; lane < 0: the lane of the caller's stream
 static int lane_for(mp_handle* h, cudaStream_t stream, int lane, mp_handle::Lane** out) {
   if (lane >= 0) {
     *out = &h->lanes[lane];
-    return MP_OK;
-  }
-  std::lock_guard<std::mutex> g(h->user_lanes_mu);
-  mp_handle::Lane& L = h->user_lanes[stream];
-  if (!L.queue_count) {
-    MP_CUDA(cudaMalloc((void**)&L.queue_count, sizeof(int)));
-    MP_CUDA(cudaMemsetAsync(L.queue_count, 0, sizeof(int), stream));
-  }
-  h->last_lane = &L;
-  *out = &L;
-  return MP_OK;
-}
-
-static int prepare_queue(mp_handle* h, KernelArgs& a, int W, cudaStream_t stream, int lane = -1) {
-  mp_handle::Lane* Lp = nullptr;
-  int rc = lane_for(h, stream, lane, &Lp);
-  if (rc) return rc;
-  mp_handle::Lane& L = *Lp;
-  rc = ensure(&L.queue, &L.cap_queue, (size_t)W);
-  if (rc) return rc;
-  if ((rc = ensure(&L.resume, &L.cap_resume, (size_t)W * kResumeLen))) return rc;
-  a.queue = L.queue;
-  a.queue_count = L.queue_count;
-  a.resume = L.resume;
-  MP_CUDA(cudaMemsetAsync(L.queue_count, 0, sizeof(int), stream));
-  return MP_OK;
-}
-
-// grid of the stiff-bucket launch: one block per batch of the longest possible queue
-static int stiff_grid(const mp_handle*, int W, int block) { return (W + block - 1) / block; }
-
-// ---- walker bucketing ------------------------------------------------------------------------
-// The step count of a walker grows with the mass that flows through the disc (log MdiscI + log delta:
-// correlation 0.58 / 0.52 with log-steps over the prior box) and, second, with the disc
-// radius (the viscous time).  In an ensemble that is spread out the lanes of a warp therefore finish at
-// very different times (prior-uniform: the slowest lane of a warp does 3.2x the mean).  With bucketing on,
-// the walkers of a launch are ordered by that key (quarter-decade bins of the mass flow, then radius) and
-// thread i evaluates walker order[i]: similar walkers share a warp.  Measured on B200: prior-uniform
-// ensembles +35 %, posterior-like spreads +5..20 %, a 1e-4 ball -2 % (the sort) -- hence opt-in.
-__global__ void bucket_key_kernel(const double* __restrict__ theta, int W, int ndim, int unlog_mask,
-                                  unsigned* __restrict__ key, int* __restrict__ id) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= W) return;
-  const double* th = theta + (size_t)i * ndim;
-  const double lm = ((unlog_mask >> 2) & 1) ? th[2] : log10(th[2]);
-  const double lr = ((unlog_mask >> 3) & 1) ? th[3] : log10(th[3]);
-  const double ld = ((unlog_mask >> 5) & 1) ? th[5] : log10(th[5]);
-  const double flow = fmin(fmax((lm + ld + 16.0) * 4.0, 0.0), 255.0);     // quarter-decade bins
-  const double rad = fmin(fmax(lr * 8192.0, 0.0), 65535.0);
-  const unsigned k = ((unsigned)(flow == flow ? flow : 0.0) << 16) | (unsigned)(rad == rad ? rad : 0.0);
-  key[i] = k;
-  id[i] = i;
-}
-
-static int bucket_walkers(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane) {
-  mp_handle::Lane* Lp = nullptr;
-  int rc0 = lane_for(h, stream, lane, &Lp);
-  if (rc0) return rc0;
-  mp_handle::Lane& L = *Lp;
-  const size_t W = (size_t)a.W;
-  if (W > L.cap_sort) {
-    cudaFree(L.key_in); cudaFree(L.key_out); cudaFree(L.id_in); cudaFree(L.id_out);
-    L.key_in = L.key_out = nullptr; L.id_in = L.id_out = nullptr; L.cap_sort = 0;
-    MP_CUDA(cudaMalloc((void**)&L.key_in, W * sizeof(unsigned)));
-    MP_CUDA(cudaMalloc((void**)&L.key_out, W * sizeof(unsigned)));
-    MP_CUDA(cudaMalloc((void**)&L.id_in, W * sizeof(int)));
-    MP_CUDA(cudaMalloc((void**)&L.id_out, W * sizeof(int)));
-    L.cap_sort = W;
-  }
-  size_t need = 0;
-  MP_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, need, L.key_in, L.key_out, L.id_in, L.id_out, (int)W, 0, 24, stream));
-  if (need > L.cap_tmp) {
-    cudaFree(L.sort_tmp);
-    L.sort_tmp = nullptr; L.cap_tmp = 0;
-    MP_CUDA(cudaMalloc(&L.sort_tmp, need));
-    L.cap_tmp = need;
-  }
-  bucket_key_kernel<<<(a.W + 255) / 256, 256, 0, stream>>>(a.theta, a.W, a.ndim, a.sp.unlog_mask, L.key_in, L.id_in);
-  MP_CUDA(cub::DeviceRadixSort::SortPairs(L.sort_tmp, need, L.key_in, L.key_out, L.id_in, L.id_out, (int)W, 0, 24, stream));
-  a.order = L.id_out;
-  return MP_OK;
-}
-
-// Every walker onto the stiff queue: a spec the explicit kernel does not implement (Bucciantini torque).
-__global__ void queue_all_kernel(int* queue, int* count, int W, const int* ids = nullptr) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < W) queue[i] = ids ? ids[i] : i;
-  if (i == 0) *count = W;
-}
-
-template <int MODE>
-static int launch_eval(mp_handle* h, KernelArgs& a, cudaStream_t stream, int lane = -1) {
-  if (a.W == 0) return MP_OK;
-  int rc = prepare_queue(h, a, a.W, stream, lane);
-  if (rc) return rc;
-  if (a.sp.bucciantini) {
-    a.resume = nullptr;                                  // every walker starts in the implicit kernel
-    queue_all_kernel<<<(a.W + 255) / 256, 256, 0, stream>>>(a.queue, a.queue_count, a.W);
-    eval_stiff_kernel<MODE, 64><<<(a.W + 63) / 64, 64, 0, stream>>>(a);
-    MP_CUDA(cudaGetLastError());
-    return MP_OK;
-  }
-  if (h->bucketing && MODE != kModeCurves && a.W >= 2048 && (rc = bucket_walkers(h, a, stream, lane))) return rc;
-  if (MODE == kModeCurves) {
-    // Curve output is dominated by the luminosity stage at up to 10 001 nodes, which a warp works through
-    // one walker at a time with one node per lane.  With few walkers (a full-grid launch is bounded by its
-    // 240 KB of output per walker) 32 walkers per warp leave most schedulers empty, so the walkers are
-    // spread one per 2..32 lanes until the launch holds ~16 warps per SM (measured: 16 384 full-grid curves,
-    // 3.5 warps per SM and 9 % FP64 pipe with dense warps).
-    int lpw = 1;
-    while (lpw < 32 && (long long)a.W * lpw * 2 <= (long long)h->sm_count * 16 * 32) lpw *= 2;
-    a.lanes_per_walker = lpw;
-    const long long threads = (long long)a.W * lpw;
-    eval_kernel<MODE, 32><<<(unsigned)((threads + 31) / 32), 32, 0, stream>>>(a);
-    eval_stiff_kernel<MODE, 32><<<stiff_grid(h, a.W, 32), 32, 0, stream>>>(a);
-    MP_CUDA(cudaGetLastError());
-    return MP_OK;
-  }
-  // small ensembles: 32-thread blocks spread the warps over more SMs
-  if (a.W <= h->sm_count * 64 * 4) {
-    eval_kernel<MODE, 32><<<(a.W + 31) / 32, 32, 0, stream>>>(a);
-    eval_stiff_kernel<MODE, 32><<<stiff_grid(h, a.W, 32), 32, 0, stream>>>(a);
   } else {
-    eval_kernel<MODE, 64><<<(a.W + 63) / 64, 64, 0, stream>>>(a);
-    eval_stiff_kernel<MODE, 64><<<stiff_grid(h, a.W, 64), 64, 0, stream>>>(a);
+    std::lock_guard<std::mutex> g(h->user_lanes_mu);
+    *out = &h->user_lanes[stream];
   }
-  MP_CUDA(cudaGetLastError());
+  h->last_lane = *out;
+  return MP_OK;
+}
+
+// Walkers per slab: a launch of more walkers than this runs as several slabs one after the other, so the work
+// space stays below ~1.5 GiB whatever the ensemble (10^7 walkers) or the node count (10 001 for full curves).
+static int slab_walkers(int Nn) {
+  const size_t per_walker = sizeof(WalkerRec) + sizeof(StiffRec) + 8 * (size_t)Nn + 16;
+  const size_t n = ((size_t)3 << 29) / per_walker;
+  return (int)std::min<size_t>(std::max<size_t>(n, 4096), (size_t)1 << 22);
+}
+
+static int ensure_work(mp_handle::Lane& L, int S, int Nn, int ndim_prop, Work& k) {
+  int rc = MP_OK;
+  if ((size_t)S > L.cap_walkers) {
+    cudaFree(L.recs); cudaFree(L.status); cudaFree(L.n_rhs); cudaFree(L.work); cudaFree(L.squeue);
+    L.recs = nullptr; L.status = L.n_rhs = L.work = nullptr; L.squeue = nullptr; L.cap_walkers = 0;
+    MP_CUDA(cudaMalloc((void**)&L.recs, (size_t)S * sizeof(WalkerRec)));      // kRecWords rows of S words
+    MP_CUDA(cudaMalloc((void**)&L.status, (size_t)S * sizeof(int)));
+    MP_CUDA(cudaMalloc((void**)&L.n_rhs, (size_t)S * sizeof(int)));
+    MP_CUDA(cudaMalloc((void**)&L.work, (size_t)S * sizeof(int)));
+    MP_CUDA(cudaMalloc((void**)&L.squeue, (size_t)S * sizeof(StiffRec)));
+    L.cap_walkers = (size_t)S;
+  }
+  if (!L.counters) MP_CUDA(cudaMalloc((void**)&L.counters, 4 * sizeof(int)));
+  if ((rc = ensure(&L.ybuf, &L.cap_ybuf, (size_t)S * Nn))) return rc;
+  if (ndim_prop > 0 && (rc = ensure(&L.prop, &L.cap_prop, (size_t)S * ndim_prop))) return rc;
+  k.stride = (int)L.cap_walkers;
+  k.recs = L.recs; k.ybuf = L.ybuf; k.status = L.status; k.n_rhs = L.n_rhs; k.work = L.work;
+  k.squeue = L.squeue; k.counters = L.counters;
+  return MP_OK;
+}
+
+// One evaluation of W walkers: setup -> advance (explicit, then the stiff queue) -> reduce, slab by slab.
+//   MOVE = false: parameters from d_theta [W][ndim]; results to `sink` (lnprob), `out` (model at data
+//                 [W][D], or curves [W][3][Nn]) and `state` (curves, optional)
+//   MOVE = true : the W movers of a stretch-move half-step described by `mv`
+template <int MODE, bool MOVE>
+static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, int W, Sink sink, double* out, double* state,
+                       const Move* mv, cudaStream_t stream, int lane = -1) {
+  if (W == 0) return MP_OK;
+  mp_handle::Lane* Lp = nullptr;
+  lane_for(h, stream, lane, &Lp);
+  const int Nn = p.dv.n_nodes, D = p.dv.n_data, ndim = p.ndim;
+  const int S = std::min(W, slab_walkers(Nn));
+  Work k;
+  std::memset(&k, 0, sizeof(k));
+  int rc = ensure_work(*Lp, S, Nn, MOVE ? ndim : 0, k);
+  if (rc) return rc;
+  Move m;
+  if (MOVE) m = *mv;
+  else std::memset(&m, 0, sizeof(m));
+  const bool coop = Nn > 64 || MODE == kModeCurves;   // by the DATASET only: a walker's lnprob never depends on the batch it is in
+  k.ws = coop ? (size_t)Nn : 1;
+  k.ns = coop ? 1 : (size_t)k.stride;
+  for (int i0 = 0; i0 < W; i0 += S) {
+    const int n = std::min(S, W - i0);
+    k.W = n;
+    Move ms = m;
+    if (MOVE) {
+      if (ms.active) ms.active += i0;
+      else ms.pos0 += i0;
+      ms.prop = Lp->prop;
+      if (ms.pack_out) ms.pack_out += (size_t)i0 * (ndim + 1);
+    }
+    Sink sk = sink;
+    if (sk.lnp) sk.lnp += i0;
+    if (sk.status) sk.status += i0;
+    if (sk.n_rhs) sk.n_rhs += i0;
+    MP_CUDA(cudaMemsetAsync(k.counters, 0, 4 * sizeof(int), stream));
+    setup_kernel<MOVE><<<(n + 127) / 128, 128, 0, stream>>>(p, k, MOVE ? nullptr : d_theta + (size_t)i0 * ndim, ms);
+    // small launches: 32-thread blocks spread the warps over more SMs
+    if (Nn == 0) {
+      // (a handle without data -- lnprior-only callers: nothing to integrate, lnlike = -0.5 * 0)
+    } else if (n <= h->sm_count * 64 * 4) {
+      advance_kernel<false, 32><<<std::min((n + 31) / 32, h->sm_count * MP_MIN_BLOCKS_32), 32, 0, stream>>>(p, k);
+      advance_kernel<true, 32><<<std::min((n + 31) / 32, h->sm_count * MP_STIFF_MIN_WARPS), 32, 0, stream>>>(p, k);
+    } else {
+      advance_kernel<false, 64><<<std::min((n + 63) / 64, h->sm_count * MP_MIN_BLOCKS_64), 64, 0, stream>>>(p, k);
+      advance_kernel<true, 64><<<std::min((n + 63) / 64, h->sm_count * MP_STIFF_MIN_WARPS / 2), 64, 0, stream>>>(p, k);
+    }
+    if (MODE == kModeCurves) {
+      reduce_curves_kernel<<<(n + 3) / 4, 128, 0, stream>>>(p, k, out + (size_t)i0 * 3 * Nn,
+                                                            state ? state + (size_t)i0 * 2 * Nn : nullptr, sk.status);
+    } else {
+      double* o = out ? out + (size_t)i0 * D : nullptr;
+      if (coop) reduce_coop_kernel<MODE, MOVE><<<(n + 3) / 4, 128, 0, stream>>>(p, k, sk, o, ms);
+      else reduce_rows_kernel<MODE, MOVE><<<(n + 63) / 64, 64, 0, stream>>>(p, k, sk, o, ms);
+    }
+    MP_CUDA(cudaGetLastError());
+  }
   return MP_OK;
 }
 
@@ -785,17 +885,14 @@ extern "C" int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32
                                       double* d_lnp, int32_t* d_status, int32_t* d_n_rhs, void* stream) {
   if (!h || (W > 0 && (!d_theta || !d_lnp))) return fail(MP_ERR_BAD_ARG, "mp_lnprob_batch_device: null pointer");
   MP_CUDA(cudaSetDevice(h->device));
-  KernelArgs a;
-  int rc = fill_args(h, a, h->data_nodes, true, ndim, W, true);
+  Problem p;
+  int rc = fill_problem(h, p, h->data_nodes, true, ndim, W, true);
   if (rc) return rc;
-  a.theta = d_theta;
-  a.lnp = d_lnp;
-  a.status = d_status;
-  a.n_rhs = d_n_rhs;
-  return launch_eval<kModeLnprob>(h, a, (cudaStream_t)stream);
+  return launch_eval<kModeLnprob, false>(h, p, d_theta, W, Sink{d_lnp, d_status, d_n_rhs}, nullptr, nullptr, nullptr,
+                                         (cudaStream_t)stream);
 }
 
-// One full wave of the explicit kernel: 8 resident 64-thread blocks per SM.
+// One full wave of the explicit integrator: 8 resident 64-thread blocks per SM.
 static int wave_walkers(const mp_handle* h) { return h->sm_count * MP_MIN_BLOCKS_64 * 64; }
 
 extern "C" int mp_lnprob_batch_async(mp_handle* h, const double* theta, int32_t W, int32_t ndim, double* lnp,
@@ -814,27 +911,25 @@ extern "C" int mp_lnprob_batch_async(mp_handle* h, const double* theta, int32_t 
     MP_CUDA(cudaMalloc((void**)&h->s_nrhs, (size_t)W * sizeof(int)));
     h->cap_w = W;
   }
-  // Large batches go through in wave-sized chunks on two alternating lanes: the H2D copy of chunk
-  // k+1 and the D2H copy of chunk k-1 overlap the kernel of chunk k (when the caller's buffers are
+  // Large batches go through in chunks of a few waves on two alternating lanes: the H2D copy of chunk
+  // k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k (when the caller's buffers are
   // pinned; pageable buffers still work, the copies just serialise).
-  const int wave = wave_walkers(h);
+  const int wave = 4 * wave_walkers(h);
   const int chunk = (W <= wave + wave / 2) ? W : wave;
-  KernelArgs a;
-  if ((rc = fill_args(h, a, h->data_nodes, true, ndim, W, true))) return rc;
+  Problem p;
+  if ((rc = fill_problem(h, p, h->data_nodes, true, ndim, W, true))) return rc;
   int k = 0;
   for (int c0 = 0; c0 < W; c0 += chunk, ++k) {
     const int lane = k & 1;
     cudaStream_t st = h->lanes[lane].stream;
     int n = W - c0;
-    if (n > chunk + chunk / 2) n = chunk;          // the last chunk absorbs a remainder below half a wave
+    if (n > chunk + chunk / 2) n = chunk;          // the last chunk absorbs a remainder below half a chunk
     MP_CUDA(cudaMemcpyAsync(h->s_theta + (size_t)c0 * ndim, theta + (size_t)c0 * ndim, (size_t)n * ndim * sizeof(double),
                             cudaMemcpyHostToDevice, st));
-    a.W = n;
-    a.theta = h->s_theta + (size_t)c0 * ndim;
-    a.lnp = h->s_lnp + c0;
-    a.status = h->s_status + c0;
-    a.n_rhs = h->s_nrhs + c0;
-    if ((rc = launch_eval<kModeLnprob>(h, a, st, lane))) return rc;
+    if ((rc = launch_eval<kModeLnprob, false>(h, p, h->s_theta + (size_t)c0 * ndim, n,
+                                              Sink{h->s_lnp + c0, h->s_status + c0, h->s_nrhs + c0}, nullptr, nullptr, nullptr,
+                                              st, lane)))
+      return rc;
     MP_CUDA(cudaMemcpyAsync(lnp + c0, h->s_lnp + c0, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (status) MP_CUDA(cudaMemcpyAsync(status + c0, h->s_status + c0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (n_rhs) MP_CUDA(cudaMemcpyAsync(n_rhs + c0, h->s_nrhs + c0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -864,30 +959,19 @@ extern "C" int mp_model_at_data(mp_handle* h, const double* pars, int32_t W, int
   if (h->D == 0) return fail(MP_ERR_NO_DATA, "mp_model_at_data: handle has no data times");
   if (W == 0) return MP_OK;
   MP_CUDA(cudaSetDevice(h->device));
-  KernelArgs a;
-  int rc = fill_args(h, a, h->data_nodes, true, ndim, W, false);
+  Problem p;
+  int rc = fill_problem(h, p, h->data_nodes, true, ndim, W, false);
   if (rc) return rc;
-  a.sp.unlog_mask = 0;  // model_lum takes physical parameters
+  p.sp.unlog_mask = 0;  // model_lum takes physical parameters
   if ((rc = ensure(&h->s_theta, &h->cap_theta, (size_t)W * MP_MAX_NDIM))) return rc;
   if ((rc = ensure(&h->s_out, &h->cap_out, (size_t)W * h->D))) return rc;
-  size_t capw = h->cap_w;
-  if (W > (int)capw) {
-    cudaFree(h->s_status);
-    h->s_status = nullptr;
-    cudaFree(h->s_lnp); cudaFree(h->s_nrhs);
-    h->s_lnp = nullptr; h->s_nrhs = nullptr; h->cap_w = 0;
-    MP_CUDA(cudaMalloc((void**)&h->s_lnp, (size_t)W * sizeof(double)));
-    MP_CUDA(cudaMalloc((void**)&h->s_status, (size_t)W * sizeof(int)));
-    MP_CUDA(cudaMalloc((void**)&h->s_nrhs, (size_t)W * sizeof(int)));
-    h->cap_w = W;
-  }
+  if ((rc = ensure(&h->s_cstatus, &h->cap_cstatus, (size_t)W))) return rc;
   MP_CUDA(cudaMemcpyAsync(h->s_theta, pars, (size_t)W * ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  a.theta = h->s_theta;
-  a.out = h->s_out;
-  a.status = h->s_status;
-  if ((rc = launch_eval<kModeModelAtData>(h, a, h->stream, 0))) return rc;
+  if ((rc = launch_eval<kModeModelAtData, false>(h, p, h->s_theta, W, Sink{nullptr, h->s_cstatus, nullptr}, h->s_out, nullptr,
+                                                 nullptr, h->stream, 0)))
+    return rc;
   MP_CUDA(cudaMemcpyAsync(out, h->s_out, (size_t)W * h->D * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-  if (status) MP_CUDA(cudaMemcpyAsync(status, h->s_status, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (status) MP_CUDA(cudaMemcpyAsync(status, h->s_cstatus, (size_t)W * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   MP_CUDA(cudaStreamSynchronize(h->stream));
   return MP_OK;
 }
@@ -918,22 +1002,23 @@ extern "C" int32_t mp_curve_nodes(const mp_handle* h, int32_t node_stride) {
   return n;
 }
 
+static int curves_on(mp_handle* h, const double* d_pars, int32_t W, int32_t ndim, int32_t node_stride, double* d_out,
+                     double* d_state, int32_t* d_status, cudaStream_t stream, int lane) {
+  DeviceNodes* dn = nullptr;
+  int rc = curve_node_set(h, node_stride, &dn);
+  if (rc) return rc;
+  Problem p;
+  if ((rc = fill_problem(h, p, *dn, false, ndim, W, false))) return rc;
+  p.sp.unlog_mask = 0;
+  return launch_eval<kModeCurves, false>(h, p, d_pars, W, Sink{nullptr, d_status, nullptr}, d_out, d_state, nullptr, stream, lane);
+}
+
 extern "C" int mp_model_curves_device(mp_handle* h, const double* d_pars, int32_t W, int32_t ndim,
                                       int32_t node_stride, double* d_out, double* d_state,
                                       int32_t* d_status, void* stream) {
   if (!h || (W > 0 && (!d_pars || !d_out))) return fail(MP_ERR_BAD_ARG, "mp_model_curves_device: null pointer");
   MP_CUDA(cudaSetDevice(h->device));
-  DeviceNodes* dn = nullptr;
-  int rc = curve_node_set(h, node_stride, &dn);
-  if (rc) return rc;
-  KernelArgs a;
-  if ((rc = fill_args(h, a, *dn, false, ndim, W, false))) return rc;
-  a.sp.unlog_mask = 0;
-  a.theta = d_pars;
-  a.out = d_out;
-  a.state = d_state;
-  a.status = d_status;
-  return launch_eval<kModeCurves>(h, a, (cudaStream_t)stream);
+  return curves_on(h, d_pars, W, ndim, node_stride, d_out, d_state, d_status, (cudaStream_t)stream, -1);
 }
 
 extern "C" int mp_model_curves(mp_handle* h, const double* pars, int32_t W, int32_t ndim, int32_t node_stride,
@@ -953,8 +1038,7 @@ extern "C" int mp_model_curves(mp_handle* h, const double* pars, int32_t W, int3
     d_status = h->s_cstatus;
   }
   MP_CUDA(cudaMemcpyAsync(h->s_theta, pars, (size_t)W * ndim * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  rc = mp_model_curves_device(h, h->s_theta, W, ndim, node_stride, h->s_out, state ? h->s_state : nullptr,
-                              d_status, h->stream);
+  rc = curves_on(h, h->s_theta, W, ndim, node_stride, h->s_out, state ? h->s_state : nullptr, d_status, h->stream, 0);
   if (!rc) {
     cudaMemcpyAsync(out, h->s_out, (size_t)W * 3 * Gs * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (state) cudaMemcpyAsync(state, h->s_state, (size_t)W * 2 * Gs * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
@@ -990,27 +1074,8 @@ extern "C" int mp_rhs_batch(const mp_model_spec* spec, const double* y, const do
   return MP_OK;
 }
 
-static int launch_stretch(mp_handle* h, StretchArgs& s, cudaStream_t stream) {
-  const int n_active = s.n_active;
-  if (n_active == 0) return MP_OK;
-  int rc;
-  if ((rc = prepare_queue(h, s.k, n_active, stream))) return rc;
-  if (s.k.sp.bucciantini) {
-    s.k.resume = nullptr;
-    queue_all_kernel<<<(n_active + 255) / 256, 256, 0, stream>>>(s.k.queue, s.k.queue_count, n_active);
-    stretch_stiff_kernel<64><<<(n_active + 63) / 64, 64, 0, stream>>>(s);
-    MP_CUDA(cudaGetLastError());
-    return MP_OK;
-  }
-  if (n_active <= h->sm_count * 64 * 4) {
-    stretch_kernel<32><<<(n_active + 31) / 32, 32, 0, stream>>>(s);
-    stretch_stiff_kernel<32><<<stiff_grid(h, n_active, 32), 32, 0, stream>>>(s);
-  } else {
-    stretch_kernel<64><<<(n_active + 63) / 64, 64, 0, stream>>>(s);
-    stretch_stiff_kernel<64><<<stiff_grid(h, n_active, 64), 64, 0, stream>>>(s);
-  }
-  MP_CUDA(cudaGetLastError());
-  return MP_OK;
+static int fill_move_problem(mp_handle* h, Problem& p, int ndim, int n_active) {
+  return fill_problem(h, p, h->data_nodes, true, ndim, n_active, true);
 }
 
 extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_lnp, int32_t nwalkers,
@@ -1022,22 +1087,23 @@ extern "C" int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_ln
       nwalkers <= 0)
     return fail(MP_ERR_BAD_ARG, "mp_stretch_half_step: null pointer or empty set");
   MP_CUDA(cudaSetDevice(h->device));
-  StretchArgs s;
-  std::memset(&s, 0, sizeof(s));
-  int rc = fill_args(h, s.k, h->data_nodes, true, ndim, n_active, true);
+  Problem p;
+  int rc = fill_move_problem(h, p, ndim, n_active);
   if (rc) return rc;
-  s.k.n_rhs = d_n_rhs;
-  s.coords = d_coords;
-  s.lnp = d_lnp;
-  s.active = d_active;
-  s.complement = d_complement;
-  s.n_active = n_active;
-  s.n_complement = n_complement;
-  s.a = a;
-  s.seed = seed;
-  s.step = step;
-  s.accepted = d_accepted;
-  return launch_stretch(h, s, (cudaStream_t)stream);
+  Move m;
+  std::memset(&m, 0, sizeof(m));
+  m.coords = d_coords;
+  m.lnp = d_lnp;
+  m.active = d_active;
+  m.complement = d_complement;
+  m.n_complement = n_complement;
+  m.a = a;
+  m.seed = seed;
+  m.step = step;
+  m.accepted = d_accepted;
+  m.n_rhs = d_n_rhs;
+  return launch_eval<kModeLnprob, true>(h, p, nullptr, n_active, Sink{nullptr, nullptr, nullptr}, nullptr, nullptr, &m,
+                                        (cudaStream_t)stream);
 }
 
 static int check_ensemble(const mp_ensemble* e, const char* who) {
@@ -1055,36 +1121,37 @@ extern "C" int mp_ensemble_half_step(mp_handle* h, const mp_ensemble* e, uint64_
   if (rc) return rc;
   if (split != 0 && split != 1) return fail(MP_ERR_BAD_ARG, "mp_ensemble_half_step: split must be 0 or 1");
   MP_CUDA(cudaSetDevice(h->device));
-  const int half = e->nwalkers / 2, m = half / e->world;
-  StretchArgs s;
-  std::memset(&s, 0, sizeof(s));
-  if ((rc = fill_args(h, s.k, h->data_nodes, true, e->ndim, m, true))) return rc;
-  s.k.n_rhs = e->n_rhs;
-  s.coords = e->coords;
-  s.lnp = e->lnp;
-  s.perm = make_split_perm(e->nwalkers, e->seed, step, e->randomize_split);
-  s.pos0 = split * half + e->rank * m;
-  s.cpos0 = (1 - split) * half;
-  s.n_active = m;
-  s.n_complement = half;
-  s.a = e->a;
-  s.seed = e->seed;
-  s.step = 2 * step + (uint64_t)split;
-  s.accepted = e->accepted;
-  s.status = e->status;
-  s.n_peers = e->n_peers;
-  for (int p = 0; p < e->n_peers; ++p) {
-    if (!e->peer_coords[p] || !e->peer_lnp[p]) return fail(MP_ERR_BAD_ARG, "mp_ensemble_half_step: null peer replica");
-    s.peer_coords[p] = e->peer_coords[p];
-    s.peer_lnp[p] = e->peer_lnp[p];
+  const int half = e->nwalkers / 2, n_mine = half / e->world;
+  Problem p;
+  if ((rc = fill_move_problem(h, p, e->ndim, n_mine))) return rc;
+  Move m;
+  std::memset(&m, 0, sizeof(m));
+  m.coords = e->coords;
+  m.lnp = e->lnp;
+  m.perm = make_split_perm(e->nwalkers, e->seed, step, e->randomize_split);
+  m.pos0 = split * half + e->rank * n_mine;
+  m.cpos0 = (1 - split) * half;
+  m.n_complement = half;
+  m.a = e->a;
+  m.seed = e->seed;
+  m.step = 2 * step + (uint64_t)split;
+  m.accepted = e->accepted;
+  m.status = e->status;
+  m.n_rhs = e->n_rhs;
+  m.n_peers = e->n_peers;
+  for (int r = 0; r < e->n_peers; ++r) {
+    if (!e->peer_coords[r] || !e->peer_lnp[r]) return fail(MP_ERR_BAD_ARG, "mp_ensemble_half_step: null peer replica");
+    m.peer_coords[r] = e->peer_coords[r];
+    m.peer_lnp[r] = e->peer_lnp[r];
   }
-  s.pack_out = e->pack_out;
+  m.pack_out = e->pack_out;
   if (e->bad_rows && e->bad_count && e->bad_capacity > 0) {
-    s.bad_rows = e->bad_rows;
-    s.bad_count = e->bad_count;
-    s.bad_capacity = e->bad_capacity;
+    m.bad_rows = e->bad_rows;
+    m.bad_count = e->bad_count;
+    m.bad_capacity = e->bad_capacity;
   }
-  return launch_stretch(h, s, (cudaStream_t)stream);
+  return launch_eval<kModeLnprob, true>(h, p, nullptr, n_mine, Sink{nullptr, nullptr, nullptr}, nullptr, nullptr, &m,
+                                        (cudaStream_t)stream);
 }
 
 extern "C" int mp_ensemble_unpack(const mp_ensemble* e, uint64_t step, int32_t split, const double* d_packed, void* stream) {
@@ -1172,8 +1239,9 @@ extern "C" int mp_last_stiff_count(mp_handle* h, int32_t* count) {
   if (!h || !count) return fail(MP_ERR_BAD_ARG, "mp_last_stiff_count: null pointer");
   MP_CUDA(cudaSetDevice(h->device));
   MP_CUDA(cudaDeviceSynchronize());
-  const mp_handle::Lane* L = h->last_lane ? h->last_lane : &h->lanes[0];
-  MP_CUDA(cudaMemcpy(count, L->queue_count, sizeof(int), cudaMemcpyDeviceToHost));
+  *count = 0;
+  if (h->last_lane && h->last_lane->counters)
+    MP_CUDA(cudaMemcpy(count, h->last_lane->counters + 2, sizeof(int), cudaMemcpyDeviceToHost));
   return MP_OK;
 }
 

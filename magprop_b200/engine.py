@@ -37,7 +37,7 @@ class Likelihood:
     """One (model spec, prior, grid, dataset) bound to one GPU."""
 
     def __init__(self, spec: A.ModelSpec, grid, x=None, y=None, yerr=None, lower=None, upper=None,
-                 device: int = 0, bucket: bool = False):
+                 device: int = 0):
         self._lib = A.load()
         self.spec = spec
         self.grid = _f64(grid, 1)
@@ -56,13 +56,6 @@ class Likelihood:
             px, py, pe = A.ptr(xs), A.ptr(ys), A.ptr(es)
         A.check(self._lib.mp_create(C.byref(spec), C.byref(self._prior), A.ptr(self.grid), self.grid.size,
                                     px, py, pe, self.D, self.device, C.byref(self._h)))
-        if bucket:
-            self.set_bucketing(True)
-
-    def set_bucketing(self, enabled: bool):
-        """Order the walkers of each large launch by a cost key so that warps hold similar walkers
-        (pays on spread-out ensembles; results keep the caller's order)."""
-        A.check(self._lib.mp_set_bucketing(self._h, 1 if enabled else 0))
 
     # -- lifetime -------------------------------------------------------------
     def close(self):

@@ -25,27 +25,53 @@ static DataView view_of(const NodeProgram& np, double t_start) {
   return dv;
 }
 
-// The kernels' bucketing on the host: explicit pass first; a walker it defers as stiff is re-run
-// from the start by the implicit variant (eval_kernel -> queue -> eval_stiff_kernel).
+// The kernels' three stages for one walker on the host: setup, advance (explicit integrator, handing over to
+// the implicit one when the walker turns stiff), reduce.  `theta` is what the caller of the corresponding
+// entry point passes (log-space for lnprob, physical for the model calls -- sp.unlog_mask says which).
 template <int MODE>
-static double evaluate_two_pass(const Spec& sp, const DataView& dv, const Walker& wk, double* buf, int& st, int& nr,
-                                double* out, double* state, const int* dat_orig) {
-  int st1 = st, nr1 = 0;
-  double r = 0.0;
-  double rec[kResumeDoubles + 64];
-  int count = 0;
-  ResumeSink sink{&count, rec, -1};
-  const bool handover = MODE != kModeCurves && !sp.bucciantini;   // as the kernels: curves restart, so does a Bucciantini spec
-  if (sp.bucciantini) st1 |= kWalkerDeferred;      // launch_eval routes such a spec to the implicit variant
-  else r = evaluate_walker<MODE, 64, false>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr,
-                                            handover ? &sink : nullptr);
-  if (st1 & kWalkerDeferred) {
-    st1 = st; nr1 = 0;
-    r = evaluate_walker<MODE, 64, true>(sp, dv, wk, true, buf, 1, st1, nr1, out, state, 1, dat_orig, nullptr, nullptr,
-                                        handover ? rec : nullptr);
+static double evaluate_staged(const Spec& sp, const DataView& dv, const double* theta, int ndim, const mp_prior_spec* pr,
+                              int& st, int& nr, double* out, double* state, const int* dat_orig) {
+  const int Nn = dv.n_nodes;
+  const double t_end = dv.node_t[Nn - 1];
+  WalkerRec r;
+  prepare_walker(sp, theta, ndim, pr && pr->enabled, pr ? pr->lower : nullptr, pr ? pr->upper : nullptr, dv.t_start, t_end, r);
+  st = r.status;
+  nr = r.n_rhs;
+  if (st & kWalkerPriorReject) return 0.0;
+  std::vector<double> row(Nn, NAN);
+  if (st == kWalkerOk) {
+    Integrator in;
+    int jn = 0;
+    bool stiff = false;
+    StiffRec q;
+    if (!sp.bucciantini) {
+      integrator_load(r, dv.t_start, in);
+      jn = drain_nodes<false>(in, 0, Nn, dv.node_t, row.data());
+      while (jn < Nn && in.status == kWalkerOk && !in.stiff) {
+        integrator_step(sp, r.w, t_end, in);
+        jn = drain_nodes<false>(in, jn, Nn, dv.node_t, row.data());
+      }
+      if (jn < Nn && in.status == kWalkerOk && in.stiff) {
+        q.t = in.t; q.y = in.omega; q.h = in.h; q.wid = 0; q.jn = jn; q.n_rhs = in.n_rhs; q.n_steps = in.n_steps;
+        stiff = true;
+      }
+    } else {
+      q.t = dv.t_start; q.y = r.y0; q.h = r.h0; q.wid = 0; q.jn = 0; q.n_rhs = r.n_rhs; q.n_steps = 0;
+      stiff = true;
+    }
+    if (stiff) {
+      integrator_load_stiff(q, in);
+      jn = drain_nodes<true>(in, q.jn, Nn, dv.node_t, row.data());
+      while (jn < Nn && in.status == kWalkerOk) {
+        radau_step(sp, r.w, t_end, in);
+        jn = drain_nodes<true>(in, jn, Nn, dv.node_t, row.data());
+      }
+    }
+    st |= in.status;
+    nr = in.n_rhs;
+    for (; jn < Nn; ++jn) row[jn] = NAN;
   }
-  st = st1; nr = nr1;
-  return r;
+  return reduce_rows<MODE>(sp, dv, r.w, row.data(), out, state, 1, dat_orig);
 }
 
 extern "C" int hs_lnprob(const mp_model_spec* ms, const mp_prior_spec* pr, const double* grid, int G,
@@ -57,25 +83,10 @@ extern "C" int hs_lnprob(const mp_model_spec* ms, const mp_prior_spec* pr, const
   if (rc) return rc;
   Spec sp = make_spec(*ms);
   DataView dv = view_of(np, grid[0]);
-  std::vector<double> buf(64);
   for (int w = 0; w < W; ++w) {
-    const double* th = theta + (size_t)w * ndim;
     int st = 0, nr = 0;
-    double out = -INFINITY;
-    if (pr->enabled && !prior_accepts(th, ndim, pr->lower, pr->upper)) {
-      st = kWalkerPriorReject;
-    } else {
-      double pars[6], de, pe, fb;
-      unpack_theta(sp, th, ndim, pars, de, pe, fb);
-      Walker wk;
-      walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
-      double chi2 = evaluate_two_pass<kModeLnprob>(sp, dv, wk, buf.data(), st, nr, nullptr, nullptr, nullptr);
-      double ll = -0.5 * chi2;
-      if (st & kWalkerIntegratorFail) ll = -INFINITY;
-      else if (!std::isfinite(ll)) { st |= kWalkerNonfiniteLnlike; ll = -INFINITY; }
-      out = ll;
-    }
-    lnp[w] = out;
+    const double chi2 = evaluate_staged<kModeLnprob>(sp, dv, theta + (size_t)w * ndim, ndim, pr, st, nr, nullptr, nullptr, nullptr);
+    lnp[w] = (st & kWalkerPriorReject) ? -INFINITY : lnlike_of(chi2, st);
     if (status) status[w] = st;
     if (nrhs) nrhs[w] = nr;
   }
@@ -95,15 +106,10 @@ extern "C" int hs_curves(const mp_model_spec* ms, const double* grid, int G, con
   sp.unlog_mask = 0;
   DataView dv = view_of(np, grid[0]);
   const int Gs = (int)node_t.size();
-  std::vector<double> buf(64);
   for (int w = 0; w < W; ++w) {
-    double pars[6], de, pe, fb;
-    unpack_theta(sp, pars_in + (size_t)w * ndim, ndim, pars, de, pe, fb);
-    Walker wk;
-    walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
     int st = 0, nr = 0;
-    evaluate_two_pass<kModeCurves>(sp, dv, wk, buf.data(), st, nr, out + (size_t)w * 3 * Gs,
-                                   state ? state + (size_t)w * 2 * Gs : nullptr, nullptr);
+    evaluate_staged<kModeCurves>(sp, dv, pars_in + (size_t)w * ndim, ndim, nullptr, st, nr, out + (size_t)w * 3 * Gs,
+                                 state ? state + (size_t)w * 2 * Gs : nullptr, nullptr);
     if (status) status[w] = st;
     if (nrhs) nrhs[w] = nr;
   }
@@ -134,14 +140,10 @@ extern "C" int hs_model_at(const mp_model_spec* ms, const double* grid, int G, c
   Spec sp = make_spec(*ms);
   sp.unlog_mask = 0;
   DataView dv = view_of(np, grid[0]);
-  std::vector<double> buf(64);
   for (int w = 0; w < W; ++w) {
-    double pars[6], de, pe, fb;
-    unpack_theta(sp, pars_in + (size_t)w * ndim, ndim, pars, de, pe, fb);
-    Walker wk;
-    walker_setup(sp, pars, de, pe, fb, dv.t_start, wk);
     int st = 0, nr = 0;
-    evaluate_two_pass<kModeModelAtData>(sp, dv, wk, buf.data(), st, nr, out + (size_t)w * D, nullptr, np.order.data());
+    evaluate_staged<kModeModelAtData>(sp, dv, pars_in + (size_t)w * ndim, ndim, nullptr, st, nr, out + (size_t)w * D, nullptr,
+                                      np.order.data());
     if (status) status[w] = st;
   }
   return 0;

@@ -318,8 +318,8 @@ def test_ten_million_walkers_config5_size(built, golden):
 
 
 def test_curves_independent_of_launch_shape(built):
-    """Curve launches spread their walkers one per 1..32 lanes depending on the launch size; a walker's curve must
-    not depend on that (same bits from a 1-, 5-, 33-, 700- and 5000-walker launch, with and without state output)."""
+    """A walker's curve must not depend on the launch it is in (same bits from a 1-, 5-, 33-, 700- and 5000-walker
+    launch, with and without state output)."""
     rng = np.random.RandomState(17)
     lk = Likelihood(A.script_model_spec(unlog=False), time_grid(None))
     pars = np.column_stack([rng.uniform(0.5, 5, 5000), rng.uniform(1, 8, 5000), 10 ** rng.uniform(-4, -2.5, 5000),
@@ -352,29 +352,34 @@ def test_async_host_pointer_calls_overlap_handles(built, golden):
         liks[name].close()
 
 
-def test_bucketing_is_transparent(built, golden):
-    """mp_set_bucketing orders the walkers of a launch by a cost key; every walker's result must be bit-identical
-    to the unbucketed launch and come back in the caller's order (prior-uniform ensemble incl. prior rejects,
-    stiff-bucket walkers and integrator failures)."""
+def test_results_do_not_depend_on_the_batch_a_walker_is_in(built, golden):
+    """The integration stage hands walkers to lanes dynamically (a lane takes its next walker off a queue when
+    its own is done), so which walkers share a warp depends on the batch: every walker's result must be
+    bit-identical whatever batch it is evaluated in, and come back in the caller's order -- prior-uniform
+    ensemble incl. prior rejects, walkers handed to the implicit integrator and integrator failures."""
     g = golden["lnprob_script"]
     rng = np.random.RandomState(21)
     W = 40000
     theta = rng.uniform(O.SCRIPT_LOWER - 0.02, O.SCRIPT_UPPER + 0.02, size=(W, 6))
-    plain = script_lik(g, "Sloped")
-    a, sa, na = plain.lnprob(theta, return_info=True)
-    plain.set_bucketing(True)
-    b, sb, nb = plain.lnprob(theta, return_info=True)
-    assert (sa == sb).all() and (na == nb).all()
-    assert ((a == b) | (np.isneginf(a) & np.isneginf(b))).all()
+    lk = script_lik(g, "Sloped")
+    a, sa, na = lk.lnprob(theta, return_info=True)
+    assert lk.last_stiff_count() > 1000
+    perm = rng.permutation(W)
+    b, sb, nb = lk.lnprob(theta[perm], return_info=True)
+    assert (sa[perm] == sb).all() and (na[perm] == nb).all()
+    assert ((a[perm] == b) | (np.isneginf(a[perm]) & np.isneginf(b))).all()
+    for lo, hi in ((0, 1), (5, 38), (1000, 1700)):
+        c, sc, nc = lk.lnprob(theta[lo:hi], return_info=True)
+        assert (sc == sa[lo:hi]).all() and (nc == na[lo:hi]).all()
+        assert ((c == a[lo:hi]) | (np.isneginf(c) & np.isneginf(a[lo:hi]))).all()
     assert 0 < (sa & A.WALKER_PRIOR_REJECT).astype(bool).sum() < W
-    # model-at-data launches are bucketed too
+    # model-at-data launches likewise
     x = g["Sloped_x"]
     pars = np.column_stack([theta[:4096, :2], 10 ** theta[:4096, 2:]])
-    mb = plain.model_at_data(pars)
-    plain.set_bucketing(False)
-    ma = plain.model_at_data(pars)
+    ma = lk.model_at_data(pars)
+    mb = lk.model_at_data(pars[::-1].copy())[::-1]
     assert np.array_equal(ma, mb, equal_nan=True) and ma.shape == (4096, x.size)
-    plain.close()
+    lk.close()
 
 
 def test_property_zero_chi2_and_beaming_linearity(built):

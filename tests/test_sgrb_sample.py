@@ -35,7 +35,7 @@ def write_limits(s, path):
     with open(path, "w") as fh:
         fh.write("pars,lower,upper\n")
         for n, lo, hi in zip(names, s["lims_lower"], s["lims_upper"]):
-            fh.write(f"{n},{lo!r},{hi!r}\n")
+            fh.write(f"{n},{float(lo)!r},{float(hi)!r}\n")
     return str(path)
 
 

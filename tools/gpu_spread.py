@@ -14,7 +14,6 @@ class O:      # the constants these tools need, from the package (the oracle is 
 g = np.load(os.path.join(ROOT, "tests/golden/lnprob_script.npz"))
 name = os.environ.get("DS", "Classic"); W = int(os.environ.get("W", 1 << 18))
 lk = Likelihood(A.script_model_spec(), time_grid(None), g[f"{name}_x"], g[f"{name}_y"], g[f"{name}_yerr"], O.SCRIPT_LOWER, O.SCRIPT_UPPER)
-if os.environ.get("BUCKET"): lk.set_bucketing(True)
 rng = np.random.RandomState(5)
 truth = O.SYNTH_TRUTHS_LOG[name]
 cases = {"ball 1e-4": truth + 1e-4 * rng.randn(W, 6),
