@@ -569,13 +569,13 @@ def extras(args, liks, data, dev, rank, world, torch, consts, A, peak):
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         out["sharded_equals_single"] = bool(int(flag.item()) == 1)
         out["sharded_equals_single_detail"] = {**eq, "nwalkers": 4096, "steps": 6, "ranks": world}
-        out[f"mcmc_nwalk{big}_sharded_peer_stores"] = mcmc(big, 5, True, "peer")
-        out[f"mcmc_nwalk{big}_sharded_packed_allgather"] = mcmc(big, 5, True, "allgather")
+        out[f"mcmc_nwalk{big}_sharded_peer_reads"] = mcmc(big, 20, True, "peer")
+        out[f"mcmc_nwalk{big}_sharded_packed_allgather"] = mcmc(big, 20, True, "allgather")
         # configs[4]: 10^7 walkers on one dataset, sharded over the ranks
         n5 = 10_000_000 - 10_000_000 % (2 * world)
-        out["config5_mcmc_1e7_walkers_sharded"] = mcmc(n5, 3, True, "peer")
+        out["config5_mcmc_1e7_walkers_sharded"] = mcmc(n5, 3, True, "auto")
     else:
-        out[f"mcmc_nwalk{big}_fused_stretch"] = mcmc(big, 5, True)
+        out[f"mcmc_nwalk{big}_fused_stretch"] = mcmc(big, 20, True)
     return out, series
 
 

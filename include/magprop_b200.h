@@ -179,11 +179,17 @@ int mp_stretch_half_step(mp_handle* h, double* d_coords, double* d_lnp, int32_t 
  * computed on the fly inside the kernel (a cycle-walking Feistel network), so every rank of a sharded run
  * derives the same split without communication.  randomize_split = 0: P = identity (fixed halves).
  *
- * Sharding: rank r of `world` moves positions [r*m, (r+1)*m) of the active half, m = n/2/world.  The rows
- * it moves must reach the other ranks' replicas before the next half-step.  Two ways:
- *   peer stores   peer_coords/peer_lnp hold the other ranks' replicas mapped into this process (mp_peer_open,
- *                 NVLink): the kernel's epilogue stores every accepted row straight into each of them; the
- *                 caller then runs mp_peer_barrier.  No collective is launched.
+ * Sharding: rank r of `world` moves positions [r*m, (r+1)*m) of the active half, m = n/2/world.  A rank's
+ * next half-step needs other ranks' moves -- the partners it draws, the current positions of the walkers it
+ * is about to move.  Two ways to get them there:
+ *   peer reads    peer_coords/peer_lnp hold the other ranks' replicas mapped into this process (mp_peer_open,
+ *                 NVLink).  A rank writes the rows it moves into its own replica only; the kernels READ a row
+ *                 from the replica of the rank that moved that walker last -- which every rank can work out,
+ *                 the ensemble order being a keyed permutation -- so only the ~2m rows a rank actually needs
+ *                 cross NVLink per half-step, not the (world-1)*m an all-gather delivers, and no collective is
+ *                 launched: the caller runs mp_peer_barrier after each half-step.  A replica is then complete
+ *                 only for the rows its rank moved last; mp_ensemble_sync completes it (for reading the chain
+ *                 out), and synced_step tells the kernels from which step on the replicas have diverged.
  *   packed rows   pack_out [m][ndim+1] receives every moved walker's (row, lnp) in position order; the
  *                 caller all-gathers the ranks' packs and scatters them with mp_ensemble_unpack (one
  *                 collective per half-step; this is also what the gloo CPU tests drive).
@@ -204,9 +210,10 @@ typedef struct mp_ensemble {
   int32_t* accepted;         /* [nwalkers] acceptance counters, or NULL */
   int32_t* status;           /* [nwalkers] or NULL */
   int32_t* n_rhs;            /* [nwalkers] or NULL */
-  int32_t n_peers;           /* entries used below (0: no peer stores) */
+  int32_t n_peers;           /* 0, or world-1: the other ranks' replicas, in rank order without this rank */
   double* peer_coords[MP_MAX_PEERS];
   double* peer_lnp[MP_MAX_PEERS];
+  uint64_t synced_step;      /* all replicas held every row when this step began (set_state / mp_ensemble_sync) */
   double* pack_out;          /* [nwalkers/2/world][ndim+1] or NULL */
   double* bad_rows;          /* [bad_capacity][ndim] or NULL */
   int32_t* bad_count;        /* [1] or NULL */
@@ -217,6 +224,9 @@ typedef struct mp_ensemble {
  * fused launch (plus the stiff-bucket launch).  Counter-based RNG (Philox4x32-10) keyed by seed with counter
  * (2*step + split, walker): any rank reproduces any walker's draws.  Enqueues on `stream`.             */
 int mp_ensemble_half_step(mp_handle* h, const mp_ensemble* ens, uint64_t step, int32_t split, void* stream);
+/* Peer-read ensembles: fetch every row another rank moved last into this replica (all ranks call it between two
+ * mp_peer_barrier calls, with `step` = the next step to run; afterwards synced_step = step).                  */
+int mp_ensemble_sync(const mp_ensemble* ens, uint64_t step, void* stream);
 /* Scatter all-gathered packs ([nwalkers/2][ndim+1], position order) of half `split` into coords / lnp.  */
 int mp_ensemble_unpack(const mp_ensemble* ens, uint64_t step, int32_t split, const double* d_packed, void* stream);
 /* The ensemble order itself: d_order[g] = P(g) for g in [0, nwalkers) (tests, host-side bookkeeping).   */
@@ -227,8 +237,8 @@ int mp_ensemble_order(int32_t nwalkers, uint64_t seed, uint64_t step, int32_t ra
  * mp_peer_alloc: cudaMalloc + export a 64-byte handle other processes pass to mp_peer_open, which maps the
  * block into the caller's address space on `device` (NVLink peer access).  mp_peer_barrier: every rank calls
  * it with the same `epoch` after a half-step; it raises flag[rank] = epoch in every peer's flag array and
- * waits until every peer has raised its own in `my_flags` -- after which all peer stores of the half-step
- * are visible.  A peer that does not arrive within ~10 s sets *d_error = 1 instead of hanging.          */
+ * waits until every peer has raised its own in `my_flags` -- after which every rank's writes of the half-step
+ * are visible to every other rank's reads.  A peer that does not arrive within ~10 s sets *d_error = 1 instead of hanging.          */
 int mp_peer_alloc(int32_t device, uint64_t bytes, void** d_ptr, unsigned char handle[64]);
 int mp_peer_open(int32_t device, const unsigned char handle[64], void** d_ptr);
 int mp_peer_close(int32_t device, void* d_ptr);

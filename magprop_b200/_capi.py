@@ -51,6 +51,7 @@ class Ensemble(C.Structure):
                 ("accepted", C.c_void_p), ("status", C.c_void_p), ("n_rhs", C.c_void_p),
                 ("n_peers", C.c_int32),
                 ("peer_coords", C.c_void_p * MP_MAX_PEERS), ("peer_lnp", C.c_void_p * MP_MAX_PEERS),
+                ("synced_step", C.c_uint64),
                 ("pack_out", C.c_void_p), ("bad_rows", C.c_void_p), ("bad_count", C.c_void_p),
                 ("bad_capacity", C.c_int32)]
 
@@ -134,6 +135,7 @@ def declare(lib):
     lib.mp_stretch_half_step.argtypes = [vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32,
                                          C.c_double, C.c_uint64, C.c_uint64, vp, vp, vp]
     lib.mp_ensemble_half_step.argtypes = [vp, C.POINTER(Ensemble), C.c_uint64, C.c_int32, vp]
+    lib.mp_ensemble_sync.argtypes = [C.POINTER(Ensemble), C.c_uint64, vp]
     lib.mp_ensemble_unpack.argtypes = [C.POINTER(Ensemble), C.c_uint64, C.c_int32, vp, vp]
     lib.mp_ensemble_order.argtypes = [C.c_int32, C.c_uint64, C.c_uint64, C.c_int32, vp, vp]
     lib.mp_peer_alloc.argtypes = [C.c_int32, C.c_uint64, C.POINTER(vp), C.c_char_p]
@@ -150,7 +152,7 @@ EXPORTS = ["mp_abi_version", "mp_device_count", "mp_last_error", "mp_create", "m
            "mp_set_prior", "mp_lnprob_batch", "mp_lnprob_batch_async", "mp_synchronize", "mp_lnprob_batch_device", "mp_model_at_data",
            "mp_curve_nodes", "mp_model_curves", "mp_model_curves_device", "mp_rhs_batch",
            "mp_stretch_half_step", "mp_fp64_peak_tflops", "mp_last_stiff_count",
-           "mp_ensemble_half_step", "mp_ensemble_unpack", "mp_ensemble_order",
+           "mp_ensemble_half_step", "mp_ensemble_sync", "mp_ensemble_unpack", "mp_ensemble_order",
            "mp_peer_alloc", "mp_peer_open", "mp_peer_close", "mp_peer_free", "mp_peer_barrier"]
 
 

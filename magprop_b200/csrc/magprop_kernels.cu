@@ -76,10 +76,18 @@ struct Move {
   int* accepted;         // [nwalkers] counters (may be null)
   int* status;           // [nwalkers] MP_WALKER_* bits of the latest proposal (may be null)
   int* n_rhs;            // [nwalkers] (may be null)
-  // replicas of (coords, lnp) on the other ranks, peer-mapped over NVLink: accepted rows are stored there too
+  // Sharded ensembles with peer-mapped replicas (NVLink): a rank writes the rows it moves into its OWN replica
+  // only, and reads a row it needs -- its movers' current positions, their partners -- from the replica of the
+  // rank that moved that walker last, which every rank can work out (the ensemble order is a keyed permutation):
+  //   moved earlier in this step (the partners of half-step 1)  ->  rank (position within the half) / n_mine
+  //   otherwise                                                 ->  the same rule with LAST step's order, unless the
+  //                                                                 replicas were synchronised since (`synced`)
+  // No collective, no remote stores; one flag barrier per half-step (mp_peer_barrier) orders the reads after the writes.
   int n_peers;
-  double* peer_coords[MP_MAX_PEERS];
-  double* peer_lnp[MP_MAX_PEERS];
+  const double* peer_coords[MP_MAX_PEERS];   // the other ranks' replicas, in rank order without this rank
+  const double* peer_lnp[MP_MAX_PEERS];
+  SplitPerm prev_perm;   // last step's ensemble order
+  int rank, n_mine, half, split, synced;
   double* pack_out;      // [n_active][ndim+1]: every mover's (row, lnp) after the move, or null
   double* bad_rows;      // proposals whose likelihood was not finite ({GRB}_bad.csv, mcmc_eqns.py:72-79)
   int* bad_count;
@@ -88,8 +96,19 @@ struct Move {
 
 struct Draw {
   double z, ua;
-  int me, partner;
+  int me, partner, pj;
 };
+// Which rank's replica holds walker w's current row (see Move).
+__device__ __forceinline__ int home_before_this_step(const Move& m, int w) {
+  if (m.synced) return m.rank;
+  return (int)(perm_inv(m.prev_perm, (uint32_t)w) % (uint32_t)m.half) / m.n_mine;
+}
+__device__ __forceinline__ const double* replica_coords(const Move& m, int home) {
+  return home == m.rank ? m.coords : m.peer_coords[home < m.rank ? home : home - 1];
+}
+__device__ __forceinline__ const double* replica_lnp(const Move& m, int home) {
+  return home == m.rank ? m.lnp : m.peer_lnp[home < m.rank ? home : home - 1];
+}
 // counter = (half-step, walker); two Philox blocks give u_z, u_partner, u_accept
 __device__ __forceinline__ Draw draw_for(const Move& m, int i) {
   Draw d;
@@ -106,6 +125,7 @@ __device__ __forceinline__ Draw draw_for(const Move& m, int i) {
   int pj = (int)(up * m.n_complement);
   if (pj >= m.n_complement) pj = m.n_complement - 1;
   d.partner = m.complement ? m.complement[pj] : (int)perm_at(m.perm, (uint32_t)(m.cpos0 + pj));
+  d.pj = pj;
   return d;
 }
 
@@ -166,8 +186,19 @@ __global__ void __launch_bounds__(128, 4) setup_kernel(const __grid_constant__ P
   if (have) {
     if (MOVE) {
       const Draw d = draw_for(m, i);
+      const double* pc = m.coords;
+      if (m.n_peers > 0) {
+        // this mover's current row into the local replica (it is about to be moved here), the partner's from its home
+        const int hm = home_before_this_step(m, d.me);
+        if (hm != m.rank) {
+          const double* src = replica_coords(m, hm);
+          for (int c = 0; c < ndim; ++c) m.coords[(size_t)d.me * ndim + c] = src[(size_t)d.me * ndim + c];
+          m.lnp[d.me] = replica_lnp(m, hm)[d.me];
+        }
+        pc = replica_coords(m, m.split == 1 ? d.pj / m.n_mine : home_before_this_step(m, d.partner));
+      }
       for (int c = 0; c < ndim; ++c) {
-        const double cc = m.coords[(size_t)d.partner * ndim + c];
+        const double cc = pc[(size_t)d.partner * ndim + c];
         const double x = m.coords[(size_t)d.me * ndim + c];
         th[c] = __dadd_rn(cc, -__dmul_rn(__dadd_rn(cc, -x), d.z));   // no FMA contraction: reproducible on the host
         m.prop[(size_t)i * ndim + c] = th[c];
@@ -371,13 +402,6 @@ __device__ __forceinline__ void deliver(const Problem& p, const Work& k, const S
   if (accept) {
     for (int c = 0; c < ndim; ++c) m.coords[(size_t)me * ndim + c] = q[c];
     m.lnp[me] = lp_new;
-    // the same row into every other rank's replica (NVLink peer stores; the caller's mp_peer_barrier
-    // makes them visible before the next half-step reads them)
-    for (int r = 0; r < m.n_peers; ++r) {
-      double* pc = m.peer_coords[r] + (size_t)me * ndim;
-      for (int c = 0; c < ndim; ++c) pc[c] = q[c];
-      m.peer_lnp[r][me] = lp_new;
-    }
     if (m.accepted) m.accepted[me] += 1;
   }
   if (m.pack_out) {
@@ -508,6 +532,18 @@ __global__ void unpack_kernel(SplitPerm perm, int pos0, int n, int ndim, const d
   const double* row = packed + (size_t)i * (ndim + 1);
   for (int d = 0; d < ndim; ++d) coords[w * ndim + d] = row[d];
   lnp[w] = row[ndim];
+}
+
+// Bring this rank's replica up to date (peer-mapped ensembles): every row whose last mover was another rank is
+// fetched from that rank's replica.  `m.prev_perm` is the order of the last completed step.
+__global__ void sync_replica_kernel(const __grid_constant__ Move m, int n, int ndim) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n) return;
+  const int home = home_before_this_step(m, w);
+  if (home == m.rank) return;
+  const double* src = replica_coords(m, home);
+  for (int c = 0; c < ndim; ++c) m.coords[(size_t)w * ndim + c] = src[(size_t)w * ndim + c];
+  m.lnp[w] = replica_lnp(m, home)[w];
 }
 
 __global__ void order_kernel(SplitPerm perm, int n, int* __restrict__ order) {
@@ -1139,6 +1175,39 @@ static int check_ensemble(const mp_ensemble* e, const char* who) {
   return MP_OK;
 }
 
+// The pull side of a peer-mapped ensemble: replicas, last step's order, whether the replicas are in sync.
+static int fill_pull(const mp_ensemble* e, uint64_t step, Move& m, const char* who) {
+  m.n_peers = e->n_peers;
+  m.rank = e->rank;
+  m.half = e->nwalkers / 2;
+  m.n_mine = m.half / e->world;
+  if (e->n_peers == 0) return MP_OK;
+  if (e->n_peers != e->world - 1) return fail(MP_ERR_BAD_ARG, std::string(who) + ": n_peers must be 0 or world - 1");
+  if (step < e->synced_step) return fail(MP_ERR_BAD_ARG, std::string(who) + ": step lies before synced_step");
+  for (int r = 0; r < e->n_peers; ++r) {
+    if (!e->peer_coords[r] || !e->peer_lnp[r]) return fail(MP_ERR_BAD_ARG, std::string(who) + ": null peer replica");
+    m.peer_coords[r] = e->peer_coords[r];
+    m.peer_lnp[r] = e->peer_lnp[r];
+  }
+  m.synced = step == e->synced_step;
+  if (!m.synced) m.prev_perm = make_split_perm(e->nwalkers, e->seed, step - 1, e->randomize_split);
+  return MP_OK;
+}
+
+extern "C" int mp_ensemble_sync(const mp_ensemble* e, uint64_t step, void* stream) {
+  int rc = check_ensemble(e, "mp_ensemble_sync");
+  if (rc) return rc;
+  Move m;
+  std::memset(&m, 0, sizeof(m));
+  m.coords = e->coords;
+  m.lnp = e->lnp;
+  if ((rc = fill_pull(e, step, m, "mp_ensemble_sync"))) return rc;
+  if (e->n_peers == 0 || m.synced) return MP_OK;
+  sync_replica_kernel<<<(e->nwalkers + 255) / 256, 256, 0, (cudaStream_t)stream>>>(m, e->nwalkers, e->ndim);
+  MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
 extern "C" int mp_ensemble_half_step(mp_handle* h, const mp_ensemble* e, uint64_t step, int32_t split, void* stream) {
   if (!h) return fail(MP_ERR_BAD_ARG, "mp_ensemble_half_step: null handle");
   int rc = check_ensemble(e, "mp_ensemble_half_step");
@@ -1162,12 +1231,8 @@ extern "C" int mp_ensemble_half_step(mp_handle* h, const mp_ensemble* e, uint64_
   m.accepted = e->accepted;
   m.status = e->status;
   m.n_rhs = e->n_rhs;
-  m.n_peers = e->n_peers;
-  for (int r = 0; r < e->n_peers; ++r) {
-    if (!e->peer_coords[r] || !e->peer_lnp[r]) return fail(MP_ERR_BAD_ARG, "mp_ensemble_half_step: null peer replica");
-    m.peer_coords[r] = e->peer_coords[r];
-    m.peer_lnp[r] = e->peer_lnp[r];
-  }
+  if ((rc = fill_pull(e, step, m, "mp_ensemble_half_step"))) return rc;
+  m.split = split;
   m.pack_out = e->pack_out;
   if (e->bad_rows && e->bad_count && e->bad_capacity > 0) {
     m.bad_rows = e->bad_rows;

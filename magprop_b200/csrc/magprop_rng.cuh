@@ -68,6 +68,24 @@ MP_RNG_HD uint32_t perm_at(const SplitPerm& p, uint32_t g) {
   } while (x >= p.n);
   return x;
 }
+// The inverse: at which position of the ensemble order walker w sits.  (Cycle-walking is symmetric: undo the
+// rounds, and walk on while the result is outside [0, n).)
+MP_RNG_HD uint32_t perm_inv(const SplitPerm& p, uint32_t w) {
+  if (!p.randomize) return w;
+  uint32_t x = w;
+  do {
+    uint32_t L = x >> p.hb, R = x & p.mask;
+    for (int r = 5; r >= 0; --r) {
+      const uint32_t F = mix32((L + (uint32_t)r * 0x9E3779B9u) ^ ((r & 1) ? p.k1 : p.k0)) & p.mask;
+      const uint32_t pR = L;
+      L = R ^ F;
+      R = pR;
+    }
+    x = (L << p.hb) | R;
+  } while (x >= p.n);
+  return x;
+}
+
 inline SplitPerm make_split_perm(int n, uint64_t seed, uint64_t step, int randomize) {
   SplitPerm p;
   p.n = (uint32_t)n;

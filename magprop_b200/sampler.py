@@ -12,11 +12,14 @@ so this module carries the minimum needed to run and measure the path:
                         accept are ONE fused launch per half-step
                         (``mp_ensemble_half_step``).  With ``torch.distributed``
                         initialised every rank holds a replica of the ensemble and
-                        moves its share of the active half; the moved rows reach the
-                        other replicas either by NVLink peer stores issued from the
-                        kernel's epilogue plus one flag barrier (``exchange="peer"``,
-                        no collective at all), or packed into ONE all-gather per
-                        half-step (``exchange="allgather"``; gloo in the CPU tests).
+                        moves its share of the active half.  ``exchange="peer"``: the
+                        replicas are mapped into one another over NVLink; a rank writes
+                        what it moves into its own replica and the kernels read the rows
+                        they need from the replica of the rank that moved them last -- no
+                        collective, one flag barrier per half-step (``sync()`` completes
+                        a replica for reading the chain out).  ``exchange="allgather"``:
+                        the moved rows packed into ONE all-gather per half-step (gloo in
+                        the CPU tests).
 
 Move semantics (Goodman & Weare 2010, as emcee's RedBlueMove implements them;
 SURVEY.md appendix C): every step the walkers are split into two halves at random
@@ -162,6 +165,9 @@ class CudaBackend:
     def unpack(self, ens, step, split, gathered):
         self.A.check(self.lib.mp_ensemble_unpack(C.byref(ens.desc), step, split, gathered.data_ptr(), self.stream() or None))
 
+    def sync(self, ens, step):
+        self.A.check(self.lib.mp_ensemble_sync(C.byref(ens.desc), step, self.stream() or None))
+
     def barrier(self, ens, epoch):
         self.A.check(self.lib.mp_peer_barrier(self.lik.device, ens._flags.data_ptr(), ens._peer_flag_ptrs, ens.rank,
                                               ens.world, epoch, ens._error.data_ptr(), self.stream() or None))
@@ -178,6 +184,7 @@ class DeviceEnsemble:
     """
 
     BAD_CAPACITY = 4096
+    PEER_READ_MAX_BYTES = 256 << 20
 
     def __init__(self, backend, nwalkers, ndim, a=2.0, seed=0, device="cuda", dist=None, randomize_split=True,
                  exchange="auto"):
@@ -201,7 +208,12 @@ class DeviceEnsemble:
         if not self.dist:
             exchange = "none"
         elif exchange == "auto":
-            exchange = "peer" if (getattr(backend, "peer_capable", False) and self.dist.get_backend() == "nccl") else "allgather"
+            # Peer reads touch the other ranks' replicas at random rows: fine while a replica stays within reach of the
+            # GPU's address-translation caches, 4x slower than the all-gather beyond (measured on 8 B200: 2^21 walkers
+            # 2.0 vs 2.4 ms per step in favour of the reads, 10^7 walkers 36.8 vs 9.4 ms against them).
+            small = nwalkers * (ndim + 1) * 8 <= self.PEER_READ_MAX_BYTES
+            exchange = "peer" if (small and getattr(backend, "peer_capable", False)
+                                  and self.dist.get_backend() == "nccl") else "allgather"
         if exchange not in ("none", "peer", "allgather"):
             raise ValueError("exchange must be 'auto', 'peer' or 'allgather'")
         self._peer_ptrs = []
@@ -221,6 +233,7 @@ class DeviceEnsemble:
             self.pack = torch.empty((self.n_mine, ndim + 1), dtype=torch.float64, device=self.device)
             self.gathered = torch.empty((half, ndim + 1), dtype=torch.float64, device=self.device)
         self.step = 0
+        self._synced_step = 0       # the replicas held every row when this step began (peer exchange)
         # ---- the C descriptor
         d = A.Ensemble()
         d.coords, d.lnp = self.coords.data_ptr(), self.lnp.data_ptr()
@@ -230,6 +243,7 @@ class DeviceEnsemble:
         d.n_peers = len(self._peer_ptrs)
         for k, (pc, pl) in enumerate(self._peer_ptrs):
             d.peer_coords[k], d.peer_lnp[k] = pc, pl
+        d.synced_step = 0
         d.pack_out = self.pack.data_ptr() if self.pack is not None else None
         d.bad_rows, d.bad_count, d.bad_capacity = self.bad_rows.data_ptr(), self.bad_count.data_ptr(), self.BAD_CAPACITY
         self.desc = d
@@ -305,10 +319,25 @@ class DeviceEnsemble:
         self._sync_ranks()
 
     def _sync_ranks(self):
-        # peers store into this replica during a half-step: nobody may start one before everybody's state is in place
+        # peers read this replica during a half-step: nobody may start one before everybody's state is in place
         if self.exchange == "peer":
             self.torch.cuda.synchronize(self.device)
             self.dist.barrier()
+            self._synced_step = self.step
+            self.desc.synced_step = self.step
+
+    def sync(self):
+        """Complete this rank's replica (``exchange="peer"``: between the half-steps a replica is current only for
+        the rows its rank moved last).  Call before reading ``coords`` / ``lnp``; a no-op for the other exchanges."""
+        if self.exchange != "peer" or self._synced_step == self.step:
+            return
+        self._epoch += 1
+        self.backend.barrier(self, self._epoch)          # every rank has finished writing ...
+        self.backend.sync(self, self.step)
+        self._epoch += 1
+        self.backend.barrier(self, self._epoch)          # ... and reading, before anyone moves on
+        self._synced_step = self.step
+        self.desc.synced_step = self.step
 
     # -- stepping ---------------------------------------------------------------------------------------
     def _half(self, split):
@@ -332,8 +361,10 @@ class DeviceEnsemble:
             self._half(1)
             self.step += 1
             if store:
+                self.sync()
                 chain[it].copy_(self.coords)
                 lps[it].copy_(self.lnp)
+        self.sync()
         return (chain, lps) if store else None
 
     def check_peers(self):
@@ -385,6 +416,7 @@ def run_concurrently(ensembles, nsteps, store=False):
                 e._half(1)
                 e.step += 1
                 if store:
+                    e.sync()
                     out[k][0][it].copy_(e.coords)
                     out[k][1][it].copy_(e.lnp)
     for e, st in zip(ensembles, streams):

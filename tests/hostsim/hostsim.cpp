@@ -180,6 +180,12 @@ extern "C" void hs_ensemble_order(int n, unsigned long long seed, unsigned long 
   const SplitPerm p = make_split_perm(n, seed, step, randomize);
   for (int g = 0; g < n; ++g) order[g] = (int)perm_at(p, (uint32_t)g);
 }
+extern "C" int hs_ensemble_order_roundtrip(int n, unsigned long long seed, unsigned long long step) {
+  const SplitPerm p = make_split_perm(n, seed, step, 1);
+  for (int g = 0; g < n; ++g)
+    if ((int)perm_inv(p, perm_at(p, (uint32_t)g)) != g) return g + 1;
+  return 0;
+}
 
 // Cost trace of the explicit pass (design aid for the launch scheduling): for each walker, the number of
 // step attempts it makes inside each chunk of NB nodes, whether / after how many attempts it is deferred as
