@@ -52,9 +52,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ensembles", type=int, default=1184,
-                    help="independent 256-walker ensembles per dataset per GPU (1184 = 148 SMs x 8 resident blocks: "
-                         "the launch is a whole number of waves)")
+    ap.add_argument("--ensembles", type=int, default=1110,
+                    help="independent 256-walker ensembles per dataset per GPU (1110 x 256 walkers = 3 x 148 SMs x 10 resident "
+                         "64-thread blocks of the integrator: every lane integrates three walkers)")
     ap.add_argument("--nwalk", type=int, default=256)
     ap.add_argument("--cpu-evals", type=int, default=0, help="CPU-baseline sample size (0: ~16 per core)")
     ap.add_argument("--curve-points", type=int, default=10 ** 6,

@@ -239,11 +239,14 @@ __global__ void __launch_bounds__(128, 4) setup_kernel(const __grid_constant__ P
 // and takes the next walker off the queue at the top of the next trip, so the lanes of a warp stay busy
 // whatever the spread of step counts in the ensemble (40 .. 10^3 over the prior box).  The cheap, divergent
 // parts (delivering nodes, hand-over, taking a walker) sit between the steps.
+// Resident blocks per SM the explicit integrator is compiled for: 10 x 64 threads = 20 warps at 96 registers.
+// (With the luminosity stage out of this kernel the spills at 96 registers are 86 bytes; measured against 8 blocks /
+// 128 registers: +7 % on 2^18-walker launches, +5 % through the host-pointer path; 12 and 14 blocks no better.)
 #ifndef MP_MIN_BLOCKS_32
-#define MP_MIN_BLOCKS_32 16
+#define MP_MIN_BLOCKS_32 20
 #endif
 #ifndef MP_MIN_BLOCKS_64
-#define MP_MIN_BLOCKS_64 8
+#define MP_MIN_BLOCKS_64 10
 #endif
 #ifndef MP_STIFF_MIN_WARPS
 #define MP_STIFF_MIN_WARPS 12     // resident warps per SM the implicit variant is compiled for
@@ -952,7 +955,7 @@ extern "C" int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32
                                          (cudaStream_t)stream);
 }
 
-// One full wave of the explicit integrator: 8 resident 64-thread blocks per SM.
+// One full wave of the explicit integrator: its resident 64-thread blocks on every SM.
 static int wave_walkers(const mp_handle* h) { return h->sm_count * MP_MIN_BLOCKS_64 * 64; }
 
 extern "C" int mp_lnprob_batch_async(mp_handle* h, const double* theta, int32_t W, int32_t ndim, double* lnp,
