@@ -384,6 +384,30 @@ MP_HD double pow_m17_seeded(double x) {
   return fma(y * e, fma(e, 4.0 / 49.0, 1.0 / 7.0), y);
 }
 
+// The same with the first-order correction only, y (1 + e/7): remainder (4/49) e^2 ~ 4e-13 with the seed's
+// e ~ 2e-6 -- three orders below the step's tolerance, which is all the integrator's disc block needs.
+MP_HD double pow_m17_seeded1(double x) {
+#if defined(__CUDA_ARCH__) && !defined(MP_POW_CVT)
+  const long long xb = __double_as_longlong(x);
+  const unsigned hi = (unsigned)(xb >> 32), lo = (unsigned)xb;
+  if (!(hi - (897u << 20) < (253u << 20))) return pow_m17_cold(x);   // outside float range, x <= 0, NaN
+  const float xf = __uint_as_float(((hi - (896u << 20)) << 3) | (lo >> 29));
+  float lg, sf;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(lg * (-1.0f / 7.0f)));
+  const unsigned fb = __float_as_uint(sf);
+  const double y = __hiloint2double((int)((fb >> 3) + (896u << 20)), (int)(fb << 29));
+#else
+  const float xf = (float)x;
+  const float sf = exp2f(log2f(xf) * (-1.0f / 7.0f));
+  if (!(xf > 1.0e-36f && xf < 1.0e37f)) return pow_m17_cold(x);
+  const double y = (double)sf;
+#endif
+  const double y2 = y * y, y4 = y2 * y2;
+  const double e = fma(-x, (y4 * y2) * y, 1.0);
+  return fma(y * (1.0 / 7.0), e, y);
+}
+
 MP_HD double rcp_fast(double x) {
 #if defined(__CUDA_ARCH__)
   return __drcp_rn(x);
@@ -620,6 +644,18 @@ MP_HD double rsqrt_pos(double x) {      // x > 0, normal
   return 1.0 / sqrt(x);
 #endif
 }
+// One Newton step on the MUFU seed: ~(3/8) 2^-44 = 2e-14 relative.  Ample inside the integrator's right-hand side
+// (its local tolerance is 4e-10; the luminosity stage keeps the third-order form).
+MP_HD double rsqrt_pos2(double x) {     // x > 0, normal
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double e = fma(x, -(r * r), 1.0);
+  return fma(0.5 * r, e, r);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 MP_HD double rcp_pos(double x) {        // 1 <= x (0 for x = inf or beyond 2^1022)
 #if defined(__CUDA_ARCH__)
   double r;
@@ -745,13 +781,13 @@ MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double 
   //   d.qa = GM^(-1/6) sqrt(A_rm) Mdisc^(-1/7)   so that  Rm = GM^(1/3) qa^2,  w = qa^3 omega (uncapped)
   //   d.ni = 2 GM^(2/3) Mdisc/(tvisc I)          so that  2 sqrt(GM Rm) Mdisc/(tvisc I) = qa d.ni
   // which removes three multiplications by constants from every evaluation.
-  const double om = rsqrt_pos(y);                              // omega
+  const double om = rsqrt_pos2(y);                             // omega
   const double iom = y * om;                                   // 1/omega
   const double rm = d.qa * d.qa;                               // uncapped Alfven radius / GM^(1/3)
   const double rcap = sp.g_kc * iom;                           // k*Rlc / GM^(1/3)
   double fast, lev;                                            // fastness w; 2 sqrt(GM Rm) Mdisc/(tvisc I) = lev * d.ni
   if (rm >= rcap) {                                            // Rm >= k*Rlc (funcs.py:109-110)
-    const double r = rsqrt_pos(om);
+    const double r = rsqrt_pos2(om);
     fast = sp.Ccap * r;
     const bool floor_ = !(rcap >= sp.g_R);
     lev = floor_ ? sp.g_floor : sp.g_cap * r;
@@ -802,7 +838,7 @@ struct Integrator {
   // implicit variant only: f, df/domega and the disc quantities at (t, omega), carried from step to step
   double J0, d0_qa, d0_ni;
   int have0;
-  // explicit variant only: the disc-mass transient exp(u0 - u(t)) at the current time, carried from
+  // explicit variant only: the disc-mass transient C exp(u0 - u(t)) at the current time, carried from
   // step to step (see disc_stages_dp5)
   double E;
   unsigned regime;               // bits 0-1: spin_g's regime bits at (t, state); bits 2-3: the regime beyond the
@@ -860,7 +896,7 @@ MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, doub
   in.stiff = 0;
   in.stiff_votes = 0;
   in.have0 = 0;
-  in.E = 1.0;                        // u(t_start) = u0
+  in.E = w.C;                        // u(t_start) = u0
   in.regime = 0u;
   in.h_resume = 0.0;
   in.J0 = in.d0_qa = in.d0_ni = 0.0;
@@ -1175,7 +1211,7 @@ MP_HD void disc_stages(const Walker& w, const double* ts, StageDisc* d) {
 }
 
 // The same for the five stage times of a Dormand-Prince step, t + (1/5, 3/10, 4/5, 8/9, 1) h, in ONE form for
-// every phase: M = K S(u) + C E with the transient E = exp(u0 - u) carried from step to step.  The stage
+// every phase: M = K S(u) + E with the transient E = C exp(u0 - u) carried from step to step.  The stage
 // fractions are multiples of 1/90, so with a = exp(-h/(90 tvisc)) the five factors are a^18, a^27, a^72,
 // a^80, a^90: ONE exponential and ten multiplications per step instead of five exponentials, applied to the
 // carried value (E_t -> E_end = E_t a^90; it drifts by ~1e-14 per step relative to itself, <= 2e-12 before
@@ -1196,7 +1232,7 @@ MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, do
     disc_stages<5>(w, ts, d);
 #pragma unroll
     for (int s = 0; s < 5; ++s) scale_for_g(sp, d[s]);
-    Eend = exp_c(w.u0 - u[4]);
+    Eend = w.C * exp_c(w.u0 - u[4]);
     return;
   }
   const double a = exp_small(fmax(dl * (-1.0 / 90.0), -40.0));
@@ -1206,9 +1242,9 @@ MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, do
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     const double S = poly10p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
-    const double M = fma(w.K, S, w.C * E[s]);
+    const double M = fma(w.K, S, E[s]);
     d[s].ni = M * w.g_tvI;
-    d[s].qa = w.g_sqrtA * pow_m17_seeded(M);
+    d[s].qa = w.g_sqrtA * pow_m17_seeded1(M);
   }
   Eend = E[4];
 }
@@ -1536,8 +1572,8 @@ MP_HD void prepare_walker(const Spec& sp, const double* theta, int ndim, bool us
   if (in.status != kWalkerOk) r.status = kWalkerIntegratorFail;
 }
 
-// The explicit integrator as prepare_walker left it.
-MP_HD void integrator_load(const WalkerRec& r, double t_start, Integrator& in) {
+// The explicit integrator as prepare_walker left it (C: the walker's disc-mass transient amplitude, Walker::C).
+MP_HD void integrator_load(const WalkerRec& r, double C, double t_start, Integrator& in) {
   in.t = t_start;
   in.omega = r.y0;
   in.h = r.h0;
@@ -1551,7 +1587,7 @@ MP_HD void integrator_load(const WalkerRec& r, double t_start, Integrator& in) {
   in.stiff_votes = 0;
   in.have0 = 0;
   in.J0 = in.d0_qa = in.d0_ni = 0.0;
-  in.E = 1.0;
+  in.E = C;
   in.regime = r.regime0;
   in.h_resume = 0.0;
   in.t0 = t_start; in.hs = 1.0;

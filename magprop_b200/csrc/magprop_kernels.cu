@@ -300,10 +300,12 @@ advance_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k
         if (STIFF) {
           const StiffRec q = k.squeue[my];
           wid = q.wid;
+          rec_load_step(k, wid, w);
           integrator_load_stiff(q, in);
           jn = q.jn;
         } else {
           wid = k.work[my];
+          rec_load_step(k, wid, w);
           const int i = wid;
           WalkerRec r;                                             // (its Walker part stays unset: see rec_load_step)
           r.y0 = __longlong_as_double((long long)MP_RWORD(y0));
@@ -313,11 +315,10 @@ advance_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k
           r.regime0 = (unsigned)rs;
           r.status = (int)(rs >> 32);
           r.n_rhs = (int)(unsigned)MP_RWORD(n_rhs);
-          integrator_load(r, p.dv.t_start, in);
+          integrator_load(r, w.C, p.dv.t_start, in);
           if (r.status != kWalkerOk) in.status = kWalkerIntegratorFail;
           jn = 0;
         }
-        rec_load_step(k, wid, w);
         row = k.ybuf + (size_t)wid * k.ws;
         jn = drain_nodes<STIFF>(in, jn, Nn, node_t, row, k.ns);      // a node at the starting time
       }

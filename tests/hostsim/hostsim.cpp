@@ -45,7 +45,7 @@ static double evaluate_staged(const Spec& sp, const DataView& dv, const double* 
     bool stiff = false;
     StiffRec q;
     if (!sp.bucciantini) {
-      integrator_load(r, dv.t_start, in);
+      integrator_load(r, r.w.C, dv.t_start, in);
       jn = drain_nodes<false>(in, 0, Nn, dv.node_t, row.data());
       while (jn < Nn && in.status == kWalkerOk && !in.stiff) {
         integrator_step(sp, r.w, t_end, in);

@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round-2 profile captures (run on one GPU under gpurun; outputs in gpurun_out/, digested into profiles/ afterwards).
+cd "$(dirname "$0")/.."
+O=gpurun_out; mkdir -p $O
+FLOPS=smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__inst_executed.sum,smsp__thread_inst_executed_per_inst_executed.ratio,gpu__time_duration.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum
+# (a) the bench's launch list: every kernel of two timed steps
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches.csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_launches.log 2>&1
+# (b) headline: the three stages, full sets + the FP64 instruction counters
+python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > /dev/null 2>&1 || exit 1
+ncu --set full --import-source on --clock-control none -k regex:advance_kernel -s 2 -c 1 -f -o $O/r02_advance_headline python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b1.log 2>&1
+ncu --metrics $FLOPS --clock-control none -k regex:"advance_kernel|setup_kernel|reduce_rows" -s 4 -c 4 --csv --log-file $O/r02_flops_headline.csv python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b2.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:reduce_rows_kernel -s 1 -c 1 -f -o $O/r02_reduce_headline python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b3.log 2>&1
+ncu --set full --import-source on --clock-control none -k regex:setup_kernel -s 1 -c 1 -f -o $O/r02_setup_headline python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b4.log 2>&1
+# (c) realistic ensembles: prior-uniform (explicit + implicit launch) and a posterior-like spread
+CASE=prior REPS=2 ncu --set full --import-source on --clock-control none -k regex:advance_kernel -s 2 -c 2 -f -o $O/r02_advance_prior python tools/gpu_one.py > $O/r02_ncu_c1.log 2>&1
+CASE=prior REPS=2 ncu --metrics $FLOPS --clock-control none -k regex:advance_kernel -s 2 -c 2 --csv --log-file $O/r02_flops_prior.csv python tools/gpu_one.py > $O/r02_ncu_c1b.log 2>&1
+CASE=s0.2 REPS=2 ncu --set full --import-source on --clock-control none -k regex:advance_kernel -s 2 -c 1 -f -o $O/r02_advance_s02 python tools/gpu_one.py > $O/r02_ncu_c2.log 2>&1
+# (d) the stretch move (setup<MOVE> forms the proposals, reduce<MOVE> accepts) and the light-curve reduce
+NWALK=262144 ncu --set full --clock-control none -k regex:"setup_kernel|reduce_rows_kernel" -s 8 -c 2 -f -o $O/r02_stretch python tools/gpu_mcmc_scale.py > $O/r02_ncu_d1.log 2>&1
+W=8192 ncu --set full --clock-control none -k regex:reduce_curves_kernel -s 1 -c 1 -f -o $O/r02_curves python tools/gpu_curves.py > $O/r02_ncu_d2.log 2>&1
+ls -la $O/r02_*
