@@ -246,6 +246,21 @@ int mp_peer_free(int32_t device, void* d_ptr);
 int mp_peer_barrier(int32_t device, uint64_t* d_my_flags, uint64_t* const* peer_flags, int32_t rank,
                     int32_t world, uint64_t epoch, int32_t* d_error, void* stream);
 
+/* ---- posterior summaries of a device-resident chain ---------------------------------------------
+ * What the reference's plot_synth.py computes from the chain file (plot_synth.py:150-166) -- pairwise
+ * correlation coefficients and the 2.5 / 50 / 97.5 percentiles of every parameter -- as reductions over the chain
+ * where the sampler left it.  d_chain is [n][ndim] row-major on `device` (the stored chain, flattened).
+ *   mp_chain_moments            column means and the covariance matrix (n-1 normalisation, as np.cov /
+ *                               np.corrcoef use); host outputs mean[ndim], cov[ndim][ndim]
+ *   mp_chain_order_statistics   the ranks[r]-th smallest value (0-based) of column `col`, exactly (radix select
+ *                               on the IEEE bit patterns); np.percentile's linear interpolation between two
+ *                               neighbouring order statistics is the caller's (it is done AFTER un-logging,
+ *                               plot_synth.py:160-166)                                                   */
+int mp_chain_moments(const double* d_chain, int64_t n, int32_t ndim, double* mean, double* cov,
+                     int32_t device, void* stream);
+int mp_chain_order_statistics(const double* d_chain, int64_t n, int32_t ndim, int32_t col,
+                              const int64_t* ranks, int32_t n_ranks, double* values, int32_t device, void* stream);
+
 /* Diagnostic: how many walkers of the most recent launch on this handle were bucketed as stiff
  * and re-run by the implicit (Radau IIA) launch.  Synchronises the device.               */
 int mp_last_stiff_count(mp_handle* h, int32_t* count);

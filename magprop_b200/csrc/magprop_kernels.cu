@@ -583,6 +583,77 @@ __global__ void peer_barrier_kernel(uint64_t* my_flags, PeerFlags pf, int rank, 
   }
 }
 
+// ---- posterior summaries of a device-resident chain (plot_synth.py:150-166) -------------------------------
+// Column means and the centred cross-products (for np.corrcoef), and exact order statistics by radix select
+// (for np.percentile): the chain never leaves the device, the host receives a few dozen numbers.
+__global__ void chain_mean_kernel(const double* __restrict__ x, long long n, int ndim, double* __restrict__ sums) {
+  __shared__ double sh[MP_MAX_NDIM][8];
+  double acc[MP_MAX_NDIM];
+  for (int d = 0; d < MP_MAX_NDIM; ++d) acc[d] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    for (int d = 0; d < ndim; ++d) acc[d] += x[i * ndim + d];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int d = 0; d < ndim; ++d) {
+    double v = acc[d];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    if (lane == 0) sh[d][wrp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < ndim) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, v);
+  }
+}
+
+__global__ void chain_cov_kernel(const double* __restrict__ x, long long n, int ndim, const double* __restrict__ mean,
+                                 double* __restrict__ cov /*[ndim][ndim], upper triangle*/) {
+  __shared__ double sh[MP_MAX_NDIM * MP_MAX_NDIM][8];
+  double acc[MP_MAX_NDIM * (MP_MAX_NDIM + 1) / 2];
+  const int npair = ndim * (ndim + 1) / 2;
+  for (int q = 0; q < npair; ++q) acc[q] = 0.0;
+  double mu[MP_MAX_NDIM];
+  for (int d = 0; d < ndim; ++d) mu[d] = mean[d];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    double c[MP_MAX_NDIM];
+    for (int d = 0; d < ndim; ++d) c[d] = x[i * ndim + d] - mu[d];
+    int q = 0;
+    for (int a = 0; a < ndim; ++a)
+      for (int b = a; b < ndim; ++b, ++q) acc[q] = fma(c[a], c[b], acc[q]);
+  }
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int q = 0; q < npair; ++q) {
+    double v = acc[q];
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    if (lane == 0) sh[q][wrp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < npair) {
+    double v = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sh[threadIdx.x][w];
+    int q = 0;
+    for (int a = 0; a < ndim; ++a)
+      for (int b = a; b < ndim; ++b, ++q)
+        if (q == (int)threadIdx.x) atomicAdd(cov + a * ndim + b, v);
+  }
+}
+
+// IEEE doubles as unsigned keys in ascending order (NaNs last).
+__device__ __forceinline__ unsigned long long order_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+// One pass of the radix select on column `col`: histogram of the 16-bit digit at `shift` over the elements whose
+// higher digits equal those of `prefix`.
+__global__ void select_hist_kernel(const double* __restrict__ x, long long n, int ndim, int col, unsigned long long prefix,
+                                   int shift, unsigned* __restrict__ hist) {
+  const unsigned long long himask = (shift >= 48) ? 0ull : (~0ull << (shift + 16));
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long key = order_key(x[i * ndim + col]);
+    if ((key & himask) == (prefix & himask)) atomicAdd(hist + (unsigned)((key >> shift) & 0xffffull), 1u);
+  }
+}
+
 // ---- the coupled right-hand side, as ODEs()/odes() return it -----------------------
 // funcs.py:75-142 / magnetar/funcs.py:33-101, operation order kept.
 __global__ void rhs_kernel(double inertia_factor, double mdot_factor, double breakup, int dipole_torque,
@@ -1325,6 +1396,80 @@ extern "C" int mp_peer_barrier(int32_t device, uint64_t* d_my_flags, uint64_t* c
   }
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_my_flags, pf, rank, world, epoch, d_error);
   MP_CUDA(cudaGetLastError());
+  return MP_OK;
+}
+
+// ---- posterior summaries on the device ---------------------------------------------------------------------
+extern "C" int mp_chain_moments(const double* d_chain, int64_t n, int32_t ndim, double* mean, double* cov, int32_t device,
+                                void* stream) {
+  if (!d_chain || !mean || !cov || n < 1 || ndim < 1 || ndim > MP_MAX_NDIM) return fail(MP_ERR_BAD_ARG, "mp_chain_moments: bad argument");
+  if (mp_device_count() <= device || device < 0) return fail(MP_ERR_CUDA, "mp_chain_moments: no such CUDA device");
+  MP_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  double* d_acc = nullptr;
+  MP_CUDA(cudaMalloc((void**)&d_acc, (ndim + ndim * ndim) * sizeof(double)));
+  cudaError_t e = cudaMemsetAsync(d_acc, 0, (ndim + ndim * ndim) * sizeof(double), st);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 1184);
+  std::vector<double> hm(ndim), hc((size_t)ndim * ndim);
+  if (e == cudaSuccess) {
+    chain_mean_kernel<<<blocks, 256, 0, st>>>(d_chain, n, ndim, d_acc);
+    e = cudaMemcpyAsync(hm.data(), d_acc, ndim * sizeof(double), cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) {
+    for (int d = 0; d < ndim; ++d) hm[d] /= (double)n;
+    e = cudaMemcpyAsync(d_acc, hm.data(), ndim * sizeof(double), cudaMemcpyHostToDevice, st);
+  }
+  if (e == cudaSuccess) {
+    chain_cov_kernel<<<blocks, 256, 0, st>>>(d_chain, n, ndim, d_acc, d_acc + ndim);
+    e = cudaMemcpyAsync(hc.data(), d_acc + ndim, (size_t)ndim * ndim * sizeof(double), cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_acc);
+  if (e != cudaSuccess) return fail(MP_ERR_CUDA, std::string("mp_chain_moments: ") + cudaGetErrorString(e));
+  for (int a = 0; a < ndim; ++a) {
+    mean[a] = hm[a];
+    for (int b = a; b < ndim; ++b) cov[a * ndim + b] = cov[b * ndim + a] = hc[(size_t)a * ndim + b] / (double)(n - 1 > 0 ? n - 1 : 1);
+  }
+  return MP_OK;
+}
+
+extern "C" int mp_chain_order_statistics(const double* d_chain, int64_t n, int32_t ndim, int32_t col, const int64_t* ranks,
+                                         int32_t n_ranks, double* values, int32_t device, void* stream) {
+  if (!d_chain || !ranks || !values || n < 1 || ndim < 1 || col < 0 || col >= ndim || n_ranks < 0)
+    return fail(MP_ERR_BAD_ARG, "mp_chain_order_statistics: bad argument");
+  if (mp_device_count() <= device || device < 0) return fail(MP_ERR_CUDA, "mp_chain_order_statistics: no such CUDA device");
+  MP_CUDA(cudaSetDevice(device));
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* d_hist = nullptr;
+  MP_CUDA(cudaMalloc((void**)&d_hist, 65536 * sizeof(unsigned)));
+  std::vector<unsigned> hist(65536);
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 1184);
+  cudaError_t e = cudaSuccess;
+  for (int r = 0; r < n_ranks && e == cudaSuccess; ++r) {
+    int64_t k = ranks[r];
+    if (k < 0 || k >= n) { cudaFree(d_hist); return fail(MP_ERR_BAD_ARG, "mp_chain_order_statistics: rank outside [0, n)"); }
+    unsigned long long prefix = 0ull;
+    for (int shift = 48; shift >= 0 && e == cudaSuccess; shift -= 16) {
+      e = cudaMemsetAsync(d_hist, 0, 65536 * sizeof(unsigned), st);
+      if (e != cudaSuccess) break;
+      select_hist_kernel<<<blocks, 256, 0, st>>>(d_chain, n, ndim, col, prefix, shift, d_hist);
+      e = cudaMemcpyAsync(hist.data(), d_hist, 65536 * sizeof(unsigned), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) break;
+      unsigned digit = 0;
+      for (; digit < 65536u; ++digit) {
+        if (k < (int64_t)hist[digit]) break;
+        k -= hist[digit];
+      }
+      prefix |= (unsigned long long)digit << shift;
+    }
+    // key -> double
+    const unsigned long long b = (prefix >> 63) ? (prefix & 0x7fffffffffffffffull) : ~prefix;
+    std::memcpy(values + r, &b, sizeof(double));
+  }
+  cudaFree(d_hist);
+  if (e != cudaSuccess) return fail(MP_ERR_CUDA, std::string("mp_chain_order_statistics: ") + cudaGetErrorString(e));
   return MP_OK;
 }
 

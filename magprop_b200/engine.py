@@ -174,3 +174,20 @@ def fp64_peak_tflops(device=0) -> float:
     v = C.c_double(0.0)
     A.check(lib.mp_fp64_peak_tflops(device, C.byref(v)))
     return v.value
+
+
+def chain_moments(d_chain: int, n: int, ndim: int, device=0, stream=0):
+    """Column means and covariance matrix of a device-resident chain [n, ndim] (raw pointer)."""
+    lib = A.load()
+    mean = np.empty(ndim); cov = np.empty((ndim, ndim))
+    A.check(lib.mp_chain_moments(d_chain, n, ndim, A.ptr(mean), A.ptr(cov), device, stream or None))
+    return mean, cov
+
+
+def chain_order_statistics(d_chain: int, n: int, ndim: int, col: int, ranks, device=0, stream=0) -> np.ndarray:
+    """Exact order statistics (0-based ranks) of one column of a device-resident chain [n, ndim]."""
+    lib = A.load()
+    ranks = np.ascontiguousarray(ranks, dtype=np.int64)
+    out = np.empty(ranks.size)
+    A.check(lib.mp_chain_order_statistics(d_chain, n, ndim, col, A.ptr(ranks), ranks.size, A.ptr(out), device, stream or None))
+    return out

@@ -1,5 +1,7 @@
 import ctypes as C
+import json
 import os
+import warnings
 import subprocess
 import sys
 
@@ -69,3 +71,22 @@ def hostsim(built):
     hs.hs_disc_S.restype = C.c_double
     hs.hs_disc_S.argtypes = [C.c_double]
     return hs
+
+
+def parity_stats(got, ref, tight):
+    e_ref, e_tight = relerr(got, ref), relerr(got, tight)
+    q = lambda e: {"max": float(e.max()), "p99": float(np.percentile(e, 99)), "median": float(np.median(e)),
+                   "n_above_1e-6": int((e > 1e-6).sum())}
+    return {"n": int(got.size), "vs_default_oracle": q(e_ref), "vs_converged_oracle": q(e_tight),
+            "default_vs_converged": q(relerr(ref, tight))}
+
+
+def report(name, stats):
+    """Error statistics where a reader of the records finds them."""
+    warnings.warn(f"parity[{name}] " + json.dumps(stats), UserWarning)
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        path = os.path.join(out, "parity_report.json")
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[name] = stats
+        json.dump(data, open(path, "w"), indent=1)

@@ -15,7 +15,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import relerr
+from conftest import parity_stats, relerr, report
 from magprop_b200 import _capi as A
 from magprop_b200.engine import Likelihood, time_grid, rhs_batch
 from oracle import magprop_oracle as O
@@ -61,6 +61,7 @@ def test_lnprob_all_golden_walkers(built, golden):
         slack = TOL_REF * np.abs(ref[ok]) + 1.5 * np.abs(ref[ok] - tight[ok])
         assert (np.abs(lnp[ok] - ref[ok]) <= slack).all()
         assert (nr[(st & A.WALKER_PRIOR_REJECT) != 0] == 0).all()      # model skipped when the prior rejects
+        report(f"lnprob_golden_{name}", parity_stats(lnp[ok], ref[ok], tight[ok]))
         lk.close()
 
 
@@ -411,3 +412,27 @@ def test_tolerance_knob_converges(built, golden):
         errs.append(relerr(out, g["lum_tight"][:4]).max())
         lk.close()
     assert errs[0] > errs[1] > errs[2] and errs[2] < 1e-8
+
+
+def test_failures_after_the_last_datum_do_not_flag_lnprob(built, golden):
+    """A deliberate difference: the reference integrates the whole grid to 1e6 s and returns
+    'flag' if LSODA fails anywhere; here the likelihood integrates only as far as the last datum, so a failure that
+    would happen later leaves lnprob finite -- while a full-grid call with the same parameters reports it."""
+    g = golden["lnprob_script"]
+    x, y, yerr = g["Humped_x"], g["Humped_y"], g["Humped_yerr"]
+    early = x <= 30.0
+    assert 3 <= early.sum() < x.size
+    theta = O.SYNTH_TRUTHS_LOG["Humped"][None, :]
+    spec = A.script_model_spec(max_steps=40)                  # enough to reach 30 s, not 1e6 s
+    lk = Likelihood(spec, time_grid(None), x[early], y[early], yerr[early], O.SCRIPT_LOWER, O.SCRIPT_UPPER)
+    lnp, st, _ = lk.lnprob(theta, return_info=True)
+    assert np.isfinite(lnp[0]) and st[0] == 0
+    want = O.lnprob(theta[0], x[early], y[early], yerr[early], O.script_spec(), O.SCRIPT_LOWER, O.SCRIPT_UPPER, tight=True)
+    assert relerr(lnp[0], want) < TOL_TIGHT
+    pars = theta.copy(); pars[:, 2:] = 10.0 ** pars[:, 2:]
+    _, st_full = lk.curves(pars, node_stride=100)
+    assert st_full[0] & A.WALKER_INTEGRATOR_FAIL              # the same budget does not reach the end of the grid
+    full = Likelihood(spec, time_grid(None), x, y, yerr, O.SCRIPT_LOWER, O.SCRIPT_UPPER)
+    lnp_full, st2, _ = full.lnprob(theta, return_info=True)
+    assert np.isneginf(lnp_full[0]) and (st2[0] & A.WALKER_INTEGRATOR_FAIL)
+    lk.close(); full.close()

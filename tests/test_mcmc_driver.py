@@ -97,3 +97,54 @@ def test_device_run_and_posterior_summary(built, golden, tmp_path):
     assert len(stats["correlations"]) == 15 and fit.shape == (4, 10001) and ymod.shape == (50,)
     assert abs(np.log10(pars[2]) + 3.0) < 0.5 and 0.3 < stats["stats"]["chi_square_red"] < 5.0
     assert stats["latex"].count("&") == 7
+
+
+@pytest.mark.gpu
+def test_posterior_summary_on_the_device_matches_the_host_one(built, golden):
+    """Row f4 as a device reduction: correlations, percentiles (exact order statistics by radix select) and the fit
+    statistics from the kernel's chi-square == the host NumPy summary of the same chain."""
+    import torch
+    from magprop_b200 import _capi as A
+    from magprop_b200.engine import Likelihood, chain_moments, chain_order_statistics, time_grid
+    from magprop_b200.sampler import DeviceEnsemble
+    from magprop_b200.synthetic import plot_synth as P
+    from oracle import magprop_oracle as O
+    g = golden["lnprob_script"]
+    x, y, yerr = g["Humped_x"], g["Humped_y"], g["Humped_yerr"]
+    lk = Likelihood(A.script_model_spec(), time_grid(None), x, y, yerr, O.SCRIPT_LOWER, O.SCRIPT_UPPER)
+    ens = DeviceEnsemble.from_likelihood(lk, 64, 6, seed=5)
+    ens.initialise(O.SYNTH_TRUTHS_LOG["Humped"] + 1e-3 * np.random.RandomState(2).randn(64, 6))
+    chain, _ = ens.run(120, store=True)                       # [120, 64, 6] on the device
+    torch.cuda.synchronize()
+    host = chain.cpu().numpy().reshape(-1, 6)
+    n = host.shape[0]
+    # the two primitives
+    mean, cov = chain_moments(chain.data_ptr(), n, 6)
+    assert np.allclose(mean, host.mean(axis=0), rtol=1e-13) and np.allclose(cov, np.cov(host.T), rtol=1e-10, atol=0)
+    ranks = [0, 1, n // 3, n - 2, n - 1]
+    for col in (0, 3, 5):
+        assert np.array_equal(chain_order_statistics(chain.data_ptr(), n, 6, col, ranks), np.sort(host[:, col])[ranks])
+    neg = torch.tensor([[-1.5, 0.0], [2.0, -0.0], [-3.0, 7.0], [0.5, -2.0]], dtype=torch.float64, device="cuda")
+    assert np.array_equal(chain_order_statistics(neg.data_ptr(), 4, 2, 0, [0, 1, 2, 3]), [-3.0, -1.5, 0.5, 2.0])
+    # the summary
+    s_dev, p_dev = P.posterior_summary_device(chain, x, y, yerr, grb="Humped")
+    s_host, p_host, _, _ = P.posterior_summary(host, x, y, yerr, grb="Humped")
+    assert np.allclose(p_dev, p_host, rtol=1e-14, atol=0)
+    assert np.allclose(s_dev["correlations"], s_host["correlations"], rtol=1e-9, atol=1e-12)
+    for k in s_host["pars"]:
+        assert np.allclose(s_dev["pars"][k], s_host["pars"][k], rtol=1e-12, atol=1e-300)
+    assert abs(s_dev["stats"]["chi_square_red"] / s_host["stats"]["chi_square_red"] - 1) < 1e-9
+    assert abs(s_dev["stats"]["aicc"] - s_host["stats"]["aicc"]) < 1e-9 * abs(s_host["stats"]["aicc"])
+    lk.close()
+
+
+def test_fit_statistics_from_lnlike():
+    from magprop_b200.magnetar import fit_stats as F
+    rng = np.random.RandomState(0)
+    y, m, e = rng.rand(30) + 1, rng.rand(30) + 1, 0.1 + rng.rand(30)
+    chi2 = np.sum(((y - m) / e) ** 2)
+    r, a = F.from_lnlike(-0.5 * chi2, 30, 6)
+    assert np.isclose(r, F.redchisq(y, m, deg=6, sd=e), rtol=1e-14) and np.isclose(a, F.aicc(y, m, e, 6), rtol=1e-14)
+    assert F.redchisq(y, m) == np.sum((y - m) ** 2) and F.redchisq(y, m, sd=e) == chi2
+    with pytest.raises(ValueError):
+        F.aicc(y, m[:-1], e, 6)

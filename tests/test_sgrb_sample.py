@@ -7,14 +7,12 @@ GPU: ``magnetar.lnprob_batch`` (packaged model, "S" grid, custom limits) against
 32 walkers per burst, incl. the 1944-point burst; the per-burst error statistics against the default- and
 the converged-tolerance oracle are reported (warnings summary + gpurun_out/parity_report.json).
 """
-import json
 import os
-import warnings
 
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, relerr
+from conftest import GOLDEN, ROOT, parity_stats, relerr, report
 
 TOL_TIGHT = 5e-7
 TOL_REF = 1e-6
@@ -88,25 +86,6 @@ def test_out_of_grid_burst_is_an_error_on_the_host(sgrb, hostsim):
                                  C.byref(n), A.ptr(scratch_i), A.ptr(np.zeros(D, np.int32)), A.ptr(scratch_d),
                                  A.ptr(np.zeros(D)), A.ptr(np.zeros(D, np.int32)))
     assert rc == A.MP_ERR_DATA_RANGE
-
-
-def parity_stats(got, ref, tight):
-    e_ref, e_tight = relerr(got, ref), relerr(got, tight)
-    q = lambda e: {"max": float(e.max()), "p99": float(np.percentile(e, 99)), "median": float(np.median(e)),
-                   "n_above_1e-6": int((e > 1e-6).sum())}
-    return {"n": int(got.size), "vs_default_oracle": q(e_ref), "vs_converged_oracle": q(e_tight),
-            "default_vs_converged": q(relerr(ref, tight))}
-
-
-def report(name, stats):
-    """Error statistics where a reader of the records finds them."""
-    warnings.warn(f"parity[{name}] " + json.dumps(stats), UserWarning)
-    out = os.path.join(ROOT, "gpurun_out")
-    if os.path.isdir(out):
-        path = os.path.join(out, "parity_report.json")
-        data = json.load(open(path)) if os.path.exists(path) else {}
-        data[name] = stats
-        json.dump(data, open(path, "w"), indent=1)
 
 
 @pytest.mark.gpu
