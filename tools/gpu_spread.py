@@ -27,6 +27,21 @@ for label, th in cases.items():
     if key == "md": th = th[np.argsort(th[:, 2] + th[:, 5])]
     if key == "r": th = th[np.argsort(th[:, 3])]
     if key == "mdr": th = th[np.lexsort((th[:, 3], np.round((th[:, 2] + th[:, 5]) * 4)))]
+    md = th[:, 2] + th[:, 5]
+    if key == "e_md": th = th[np.lexsort((md, np.round(th[:, 4] * 4)))]
+    if key == "md_e": th = th[np.lexsort((th[:, 4], np.round(md * 4)))]
+    if key == "e2_md": th = th[np.lexsort((md, np.round(th[:, 4] * 2)))]
+    if key == "md2_e": th = th[np.lexsort((th[:, 4], np.round(md * 2)))]
+    if key == "e_r": th = th[np.lexsort((th[:, 3], np.round(th[:, 4] * 4)))]
+    if key == "m": th = th[np.argsort(th[:, 2])]
+    if key == "d": th = th[np.argsort(th[:, 5])]
+    if key == "e_d": th = th[np.lexsort((th[:, 5], np.round(th[:, 4] * 4)))]
+    if key == "e_m": th = th[np.lexsort((th[:, 2], np.round(th[:, 4] * 4)))]
+    if key == "b": th = th[np.argsort(th[:, 0])]
+    if key == "p": th = th[np.argsort(th[:, 1])]
+    if key == "e": th = th[np.argsort(th[:, 4])]
+    if key == "bp": th = th[np.lexsort((th[:, 1], np.round(np.log10(th[:, 0]) * 8)))]
+    if key == "all": th = th[np.lexsort((th[:, 4], np.round(th[:, 3] * 4), np.round(th[:, 1] * 2), np.round(np.log10(th[:, 0]) * 4), np.round((th[:, 2] + th[:, 5]) * 2)))]
     d_th = torch.from_numpy(np.ascontiguousarray(th)).cuda(); d_l = torch.empty(W, dtype=torch.float64, device="cuda"); d_n = torch.empty(W, dtype=torch.int32, device="cuda")
     for _ in range(2): lk.lnprob_device(d_th.data_ptr(), W, 6, d_l.data_ptr(), 0, d_n.data_ptr())
     torch.cuda.synchronize()
