@@ -1310,7 +1310,7 @@ struct RadauC {
 MP_HD void spin_fJ(const Spec& sp, const Walker& w, const StageDisc& d, double omega, double& f, double& J,
                    unsigned& side) {
   const double rm = d.qa * d.qa;
-  const double r = rsqrt_pos(omega);
+  const double r = rsqrt_pos2(omega);                         // (integrator-grade: 2e-14, as in spin_g)
   const double hio = -0.5 * (r * r);                           // -1/(2 omega)
   const bool capped = rm * omega >= sp.kc;
   const double wq = (rm * d.qa) * sp.inv_sqrtGM;
@@ -1328,7 +1328,7 @@ MP_HD void spin_fJ(const Spec& sp, const Walker& w, const StageDisc& d, double o
   if (x > 19.1) { th = 1.0; sech2 = 0.0; }
   else if (x < -19.1) { th = -1.0; sech2 = 0.0; }
   else {
-    const double rr = rcp_pos(exp_small(x + x) + 1.0);
+    const double rr = rcp_pos2(exp_small10(x + x) + 1.0);
     th = fma(-2.0, rr, 1.0);
     sech2 = 4.0 * rr * (1.0 - rr);
   }
@@ -1405,6 +1405,13 @@ MP_HD void radau_step(const Spec& sp, const Walker& w, double t_end, Integrator&
     const double dz = fmax(fabs(d1), fmax(fabs(d2), fabs(d3)));
     if (!(dz == dz)) break;
     if (dz <= 1.0e-3 * sk + 4.0e-16 * fabs(z3)) { converged = true; ++it; break; }
+#ifndef MP_NEWTON_KAPPA
+#define MP_NEWTON_KAPPA 0.03
+#endif
+    // (radau5's stopping rule: with the contraction rate theta = |dZ_k| / |dZ_k-1| the error left after this update
+    // is about theta/(1-theta) |dZ_k|; the Newton iteration is quadratic here -- the Jacobians are fresh -- so that is
+    // usually met one iteration before the update itself is below the tolerance: 2 instead of 3 iterations per step)
+    if (it >= 1 && dz < 0.5 * dz_prev && (dz / (dz_prev - dz)) * dz <= MP_NEWTON_KAPPA * sk) { converged = true; ++it; break; }
     if (it >= 2 && dz > 2.0 * dz_prev) break;      // diverging
     dz_prev = dz;
   }
