@@ -80,6 +80,7 @@ struct Work {
 // a 1e-4 ball unchanged; results do not depend on the order (tested).
 constexpr int kOrderBuckets = 32 * 256;
 constexpr int kOrderMinWalkers = 8192;
+constexpr int kCoopSmallWalkers = 2048;   // launches up to this size run stage 3 with a warp per walker (see reduce_coop_kernel)
 constexpr int kOrderTightBuckets = 8;
 __device__ __forceinline__ int order_key_of(const Spec& sp, const double* th) {
   const float le = ((sp.unlog_mask >> 4) & 1) ? (float)th[4] : __log10f((float)th[4]);
@@ -566,7 +567,11 @@ __global__ void __launch_bounds__(64, 12) reduce_rows_kernel(const __grid_consta
 // is a warp-shuffle reduction over the data.  Used for the large datasets (the short-GRB sample: up to 1944
 // points, ~2 nodes per datum), and it is what makes a small ensemble on such a burst run at the speed of the
 // integration alone instead of one thread walking thousands of nodes.
-template <int MODE, bool MOVE>
+// ORDERED = true: the residuals are summed in datum order (passed round the warp by shuffles) instead of by a tree,
+// which reproduces reduce_rows_kernel's chi-square bit for bit: small launches on SMALL datasets use this form --
+// a 128-walker half-step then spends 5 us here instead of 80 -- while large ones keep one thread per walker, and a
+// walker's lnprob still does not depend on the size of the batch it is in.
+template <int MODE, bool MOVE, bool ORDERED>
 __global__ void __launch_bounds__(128) reduce_coop_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k,
                                                           const __grid_constant__ Sink s, double* __restrict__ out,
                                                           const __grid_constant__ Move m) {
@@ -578,29 +583,37 @@ __global__ void __launch_bounds__(128) reduce_coop_kernel(const __grid_constant_
   if (!(st & kWalkerPriorReject)) {
     Walker w;
     rec_load_lum(k, i, w);                                     // (every lane the same words: broadcast loads)
-    const double* row = k.ybuf + (size_t)i * k.ws;             // node-minor: k.ns == 1
+    const double* row = k.ybuf + (size_t)i * k.ws;
     const DataView& dv = p.dv;
     for (int d0 = 0; d0 < dv.n_data; d0 += 32) {
       const int d = d0 + lane;
+      double r = 0.0;
       if (d < dv.n_data) {
         const int lo = dv.dat_lo[d];
         const double dx = dv.dat_dx[d];
         double M, om;
-        const double L_lo = node_luminosity(p.sp, w, dv.node_t[lo], dv.t_start, row[lo], false, M, om).tot;
+        const double L_lo = node_luminosity(p.sp, w, dv.node_t[lo], dv.t_start, row[lo * k.ns], false, M, om).tot;
         double mod = L_lo;                                     // datum sits on a grid node
         if (dx != 0.0) {
-          const double L_hi = node_luminosity(p.sp, w, dv.node_t[lo + 1], dv.t_start, row[lo + 1], false, M, om).tot;
+          const double L_hi = node_luminosity(p.sp, w, dv.node_t[lo + 1], dv.t_start, row[(lo + 1) * k.ns], false, M, om).tot;
           mod = fma(L_hi - L_lo, dv.dat_w[d], L_lo);           // np.interp: slope*(x-x_lo)+y_lo
         }
-        if (MODE == kModeLnprob) {
-          const double r = fma(-mod, dv.dat_c[d], dv.dat_ys[d]);   // (y - mod/1e50)/yerr
-          chi2 = fma(r, r, chi2);
+        if (MODE == kModeLnprob) r = fma(-mod, dv.dat_c[d], dv.dat_ys[d]);   // (y - mod/1e50)/yerr
+        else out[(size_t)i * dv.n_data + (p.dat_orig ? p.dat_orig[d] : d)] = mod * 1.0e-50;
+      }
+      if (MODE == kModeLnprob) {
+        if (ORDERED) {
+          const int cnt = min(32, dv.n_data - d0);
+          for (int l = 0; l < cnt; ++l) {
+            const double rl = __shfl_sync(kFull, r, l);
+            chi2 = fma(rl, rl, chi2);
+          }
         } else {
-          out[(size_t)i * dv.n_data + (p.dat_orig ? p.dat_orig[d] : d)] = mod * 1.0e-50;
+          chi2 = fma(r, r, chi2);
         }
       }
     }
-    if (MODE == kModeLnprob)
+    if (MODE == kModeLnprob && !ORDERED)
       for (int off = 16; off > 0; off >>= 1) chi2 += __shfl_xor_sync(kFull, chi2, off);   // same value on every lane
   }
   if (lane != 0) return;
@@ -1132,7 +1145,8 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
                                                             state ? state + (size_t)i0 * 2 * Nn : nullptr, sk.status);
     } else {
       double* o = out ? out + (size_t)i0 * D : nullptr;
-      if (coop) reduce_coop_kernel<MODE, MOVE><<<(n + 3) / 4, 128, 0, stream>>>(p, k, sk, o, ms);
+      if (coop) reduce_coop_kernel<MODE, MOVE, false><<<(n + 3) / 4, 128, 0, stream>>>(p, k, sk, o, ms);
+      else if (n <= kCoopSmallWalkers) reduce_coop_kernel<MODE, MOVE, true><<<(n + 3) / 4, 128, 0, stream>>>(p, k, sk, o, ms);
       else reduce_rows_kernel<MODE, MOVE><<<(n + 63) / 64, 64, 0, stream>>>(p, k, sk, o, ms);
     }
     MP_CUDA(cudaGetLastError());
