@@ -39,10 +39,10 @@ DATASETS = ("Classic", "Sloped", "Stuttering")
 METRIC = "walker_lnprob_evals_per_sec"
 UNIT = "evals/s"
 F_RHS, F_LUM, F_CHI = 440.0, 400.0, 12.0      # flop per unit of the REFERENCE's formulation
-# What the kernel executes per right-hand-side evaluation, counted by ncu on this workload
-# (profiles/r01_executed.json, written from the committed ncu capture by tools/ncu_digest.py):
-# flop = 2*DFMA + DMUL + DADD thread instructions / (walkers * RHS evaluations).
-with open(os.path.join(ROOT, "profiles", "r01_executed.json")) as _f:
+# What the kernels execute, counted by ncu on this workload (profiles/r02_executed.json, written from the committed
+# counter pass profiles/r02_flops_headline.csv by tools/make_executed.py): flop = 2*DFMA + DMUL + DADD thread
+# instructions, per right-hand-side evaluation for the integrator and per evaluation for the setup / reduce stages.
+with open(os.path.join(ROOT, "profiles", "r02_executed.json")) as _f:
     NCU = json.load(_f)
 
 
@@ -351,17 +351,23 @@ def run_ours(args):
     # FP64 roofline of eval_kernel: executed flop (ncu-counted per RHS evaluation, RHS evaluations
     # counted live on the device) over the live-measured launch time, against the live DFMA peak.
     rhs_per_s = (value / world) * mean_nrhs
-    executed = rhs_per_s * NCU["flop_per_rhs"] / 1e12
+    stage_flop = NCU["stage_flop_per_eval"]["setup"] + NCU["stage_flop_per_eval"]["reduce"]
+    executed = (rhs_per_s * NCU["flop_per_rhs"] + (value / world) * stage_flop) / 1e12
     roofline = {
         "bound": "fp64", "achieved": executed, "peak": peak, "unit": "TFLOP/s",
         "frac": executed / peak if peak else None,
         "traffic": NCU.get("dram_bytes_per_launch"),
         "kernel": "mp::advance_kernel<false,64> (the explicit spin integrator; setup and reduce kernels are inside the timed launch)",
-        "how": "achieved = (RHS evaluations/s, counted on the device) x (FP64 flop per RHS evaluation that the kernel "
-               "executes, ncu: 2*DFMA+DMUL+DADD); peak = live DFMA micro-benchmark on this GPU (MEASURED_PEAKS.json "
-               "has no FP64 entry); launch time from CUDA events on the launching stream",
+        "how": "achieved = executed FP64 flop of the timed launches (ncu: 2*DFMA+DMUL+DADD thread instructions -- per RHS "
+               "evaluation for the integrator, times the RHS evaluations counted live on the device, plus the setup and reduce "
+               "stages' per evaluation) / launch time from CUDA events on the launching stream; peak = live DFMA micro-benchmark "
+               "on this GPU (MEASURED_PEAKS.json has no FP64 entry).  The fraction is bounded by the instruction mix: 43 % of the "
+               "integrator's FP64 arithmetic instructions are plain multiplies (1 flop per pipe slot instead of 2), so a fully "
+               "busy pipe would read 0.76; fp64_pipe_active_pct_ncu is the pipe's occupancy itself",
         "flop_per_rhs_executed": NCU["flop_per_rhs"], "fp64_inst_per_rhs": NCU["fp64_inst_per_rhs"],
+        "setup_plus_reduce_flop_per_eval": stage_flop,
         "fp64_pipe_active_pct_ncu": NCU["fp64_pipe_active_pct"], "ncu_source": NCU["source"],
+        "stage_ms_per_step_ncu": NCU["stage_ms_per_step"],
         "mean_rhs_per_eval": mean_nrhs, "hbm_bytes_per_eval": 48 + 8 + 4,
         "survey_8d_convention": {
             "note": "SURVEY.md 8(d) counts the reference's formulation (440 flop per RHS: generic pow/tanh/sqrt); "
@@ -379,7 +385,8 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * 6 * 8 * len(DATASETS),
                     "d2h_bytes_per_step": W * 8 * len(DATASETS)},
-            "gpu_launches": 4 * args.steps * len(DATASETS),   # setup, advance (explicit), advance (implicit), reduce per dataset per step
+            # per dataset per step: setup, work-list scan + scatter, advance (explicit), advance (implicit), reduce
+            "gpu_launches": 6 * args.steps * len(DATASETS),
             "clocks": clocks,
             "nonfinite_lnprob": bad,
             "wall_s_timed_region": wall,
@@ -428,7 +435,8 @@ def extras(args, liks, data, dev, rank, world, torch, consts, A, peak):
 
     def as_series(r, what):
         """A first-class line for a realistic ensemble: the headline's metric with its own roofline block."""
-        executed = r["evals_per_s"] * r["mean_rhs"] * NCU["flop_per_rhs"] / 1e12
+        executed = r["evals_per_s"] * (r["mean_rhs"] * NCU["flop_per_rhs"] + NCU["stage_flop_per_eval"]["setup"]
+                                       + NCU["stage_flop_per_eval"]["reduce"]) / 1e12
         return {"metric": METRIC, "unit": UNIT, "value": r["evals_per_s"] * world, "per_gpu": r["evals_per_s"], "n_gpus": world,
                 "workload": what, "walkers_per_gpu": r["walkers"], "ms_per_launch": r["ms"],
                 "roofline": {"bound": "fp64", "achieved": executed, "peak": peak, "unit": "TFLOP/s",

@@ -8,7 +8,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 # (b) headline: the three stages, full sets + the FP64 instruction counters
 python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > /dev/null 2>&1 || exit 1
 ncu --set full --import-source on --clock-control none -k regex:advance_kernel -s 2 -c 1 -f -o $O/r02_advance_headline python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b1.log 2>&1
-ncu --metrics $FLOPS --clock-control none -k regex:"advance_kernel|setup_kernel|reduce_rows" -s 4 -c 4 --csv --log-file $O/r02_flops_headline.csv python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b2.log 2>&1
+# (one whole step: the 3 datasets x (setup, advance, advance<implicit>, reduce); bench's own JSON line carries the RHS count)
+ncu --metrics $FLOPS --clock-control none -k regex:"advance_kernel|setup_kernel|reduce_rows" -s 0 -c 12 --csv --log-file $O/r02_flops_headline.csv python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b2.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:reduce_rows_kernel -s 1 -c 1 -f -o $O/r02_reduce_headline python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b3.log 2>&1
 ncu --set full --import-source on --clock-control none -k regex:setup_kernel -s 1 -c 1 -f -o $O/r02_setup_headline python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > $O/r02_ncu_b4.log 2>&1
 # (c) realistic ensembles: prior-uniform (explicit + implicit launch) and a posterior-like spread
