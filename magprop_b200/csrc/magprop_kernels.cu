@@ -67,19 +67,25 @@ struct Work {
   StiffRec* squeue;    // [W] walkers for the implicit integrator
   int* counters;       // [0] walkers in `work`, [1] next to hand out, [2] walkers in `squeue`, [3] next to hand out
   // ordering of `work` (large launches): per-walker bucket key and the bucket histogram / cursors
-  int* key;            // [W] or null: no ordering, walkers are appended as they come
-  int* hist;           // [kOrderBuckets]
-};
+  int* key;            // [W] bucket key of every walker
+  int* hist;           // [kOrderBuckets + 3]: bucket counts / offsets, "tight" flag, tight cursor, block ticket
+  int* slot_wid;       // [W] or null: the stages index their work space by SLOT; slot s holds walker slot_wid[s]
+};                     //          (null: slot = walker, launches too small to be worth ordering)
 
 // The order in which the integrator takes the walkers of a large launch.  Lanes that start together run through
-// the same phases of the integration together only if their walkers are alike, so `work` is laid out by a key of
+// the same phases of the integration together only if their walkers are alike, so the walkers of a large launch are
+// given SLOTS -- the index under which all three stages keep a walker's record, node values and status, so that
+// neighbouring lanes also touch neighbouring memory -- in the order of a key of
 // the two parameter combinations that set a walker's timeline: the fallback time scale epsilon (quarter-decade
 // bins, ascending -- which also puts the long integrations first) and, within a bin, the mass that flows through
 // the disc, M_disc * delta (1/24-decade bins).  A counting sort: histogram in setup_kernel, one scan, one scatter.
 // Measured on 2^18 walkers against the unordered list: prior-uniform +16 %, posterior-like spreads +10..18 %,
 // a 1e-4 ball unchanged; results do not depend on the order (tested).
 constexpr int kOrderBuckets = 32 * 256;
-constexpr int kOrderMinWalkers = 8192;
+#ifndef MP_ORDER_MIN_WALKERS
+#define MP_ORDER_MIN_WALKERS 8192
+#endif
+constexpr int kOrderMinWalkers = MP_ORDER_MIN_WALKERS;
 constexpr int kCoopSmallWalkers = 2048;   // launches up to this size run stage 3 with a warp per walker (see reduce_coop_kernel)
 constexpr int kOrderTightBuckets = 8;
 __device__ __forceinline__ int order_key_of(const Spec& sp, const double* th) {
@@ -88,7 +94,8 @@ __device__ __forceinline__ int order_key_of(const Spec& sp, const double* th) {
   const float ld = ((sp.unlog_mask >> 5) & 1) ? (float)th[5] : __log10f((float)th[5]);
   const float eb = fminf(fmaxf((le + 4.0f) * 4.0f, 0.0f), 31.0f);
   const float mb = fminf(fmaxf((lm + ld + 10.0f) * 24.0f, 0.0f), 255.0f);
-  return ((eb == eb) ? (int)eb : 0) * 256 + ((mb == mb) ? (int)mb : 0);
+  const int ie = (eb == eb) ? (int)eb : 0, im = (mb == mb) ? (int)mb : 0;
+  return ie * 256 + ((ie & 1) ? 255 - im : im);      // zig-zag: neighbouring buckets across an epsilon boundary are alike
 }
 // The threads of a block claim slots of their keys' counters: lanes with the same key share one atomic, and when
 // the whole block holds one key (a tight ensemble: every walker in the same bucket) so do its warps -- otherwise
@@ -134,46 +141,45 @@ __device__ __forceinline__ int block_claim_by_key(bool want, int key, int* count
   }
   return pos;
 }
-__global__ void __launch_bounds__(1024) order_scan_kernel(int* __restrict__ hist, int* __restrict__ counters) {
-  // exclusive scan of the bucket histogram in place (hist[b] becomes the first slot of bucket b); total -> counters[0].
-  // An ensemble that occupies only a handful of buckets is tight enough to be taken as it comes: hist[kOrderBuckets]
-  // tells the scatter so, which then appends in index order (contiguous walkers per warp, no bucket cursors).
-  __shared__ int part[1024];
+// Exclusive scan of the bucket histogram in place (hist[b] becomes the first slot of bucket b), by the NT threads of
+// one block.  An ensemble that occupies only a handful of buckets is tight enough to be taken as it comes:
+// hist[kOrderBuckets] tells the scatter so, which then hands out the slots in index order (cursor: hist[kOrderBuckets + 1]).
+template <int NT>
+__device__ __forceinline__ void scan_buckets(int* __restrict__ hist) {
+  __shared__ int part[NT];
   __shared__ int occupied;
-  constexpr int per = kOrderBuckets / 1024;
-  int local[per], sum = 0, nz = 0;
+  constexpr int per = kOrderBuckets / NT;
+  const int base = threadIdx.x * per;
+  int sum = 0, nz = 0;
   if (threadIdx.x == 0) occupied = 0;
-  for (int c = 0; c < per; ++c) { local[c] = hist[threadIdx.x * per + c]; sum += local[c]; nz += local[c] != 0; }
+  for (int c = 0; c < per; ++c) { const int v = __ldcg(hist + base + c); sum += v; nz += v != 0; }   // (written by other blocks' atomics: read at L2)
   part[threadIdx.x] = sum;
   __syncthreads();
   if (nz) atomicAdd(&occupied, nz);
   __syncthreads();
   if (occupied <= kOrderTightBuckets) {
-    if (threadIdx.x == 0) { hist[kOrderBuckets] = 1; counters[0] = 0; }
+    if (threadIdx.x == 0) hist[kOrderBuckets] = 1;
     return;
   }
-  if (threadIdx.x == 0) hist[kOrderBuckets] = 0;
-  for (int off = 1; off < 1024; off <<= 1) {
+  for (int off = 1; off < NT; off <<= 1) {
     const int v = (threadIdx.x >= off) ? part[threadIdx.x - off] : 0;
     __syncthreads();
     part[threadIdx.x] += v;
     __syncthreads();
   }
   int run = part[threadIdx.x] - sum;
-  for (int c = 0; c < per; ++c) { hist[threadIdx.x * per + c] = run; run += local[c]; }
-  if (threadIdx.x == 1023) counters[0] = part[1023];
+  for (int c = 0; c < per; ++c) { const int v = __ldcg(hist + base + c); hist[base + c] = run; run += v; }
 }
-__global__ void order_scatter_kernel(int W, const int* __restrict__ key, int* __restrict__ cursor, int* __restrict__ work,
-                                     int* __restrict__ counters) {
+__global__ void order_scatter_kernel(int W, const int* __restrict__ key, int* __restrict__ cursor, int* __restrict__ slot_wid) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int kk = (i < W) ? key[i] : -1;
   if (cursor[kOrderBuckets]) {                       // tight ensemble: as it comes
-    const int we = warp_append(kk >= 0, counters + 0);
-    if (kk >= 0) work[we] = i;
+    const int we = warp_append(kk >= 0, cursor + kOrderBuckets + 1);
+    if (kk >= 0) slot_wid[we] = i;
     return;
   }
   const int pos = block_claim_by_key(kk >= 0, kk, cursor);
-  if (kk >= 0) work[pos] = i;
+  if (kk >= 0) slot_wid[pos] = i;
 }
 
 // The stretch move wrapped around an evaluation (mp_stretch_half_step / mp_ensemble_half_step):
@@ -283,37 +289,73 @@ __device__ __forceinline__ void rec_load_lum(const Work& k, int i, Walker& w) {
 }
 
 // ---- stage 1: setup ---------------------------------------------------------------------------------
+// The stretch proposal of mover i (see Move): q = c - (c - s) z, kept in m.prop[i] for the accept step.  With
+// peer-mapped replicas the mover's current row is first brought into the local replica (it is about to be moved
+// here) and the partner's row is read from its home.
+__device__ __forceinline__ void propose(const Move& m, int i, int ndim, double* th) {
+  const Draw d = draw_for(m, i);
+  const double* pc = m.coords;
+  if (m.n_peers > 0) {
+    const int hm = home_before_this_step(m, d.me);
+    if (hm != m.rank) {
+      const double* src = replica_coords(m, hm);
+      for (int c = 0; c < ndim; ++c) m.coords[(size_t)d.me * ndim + c] = src[(size_t)d.me * ndim + c];
+      m.lnp[d.me] = replica_lnp(m, hm)[d.me];
+    }
+    pc = replica_coords(m, m.split == 1 ? d.pj / m.n_mine : home_before_this_step(m, d.partner));
+  }
+  for (int c = 0; c < ndim; ++c) {
+    const double cc = pc[(size_t)d.partner * ndim + c];
+    const double x = m.coords[(size_t)d.me * ndim + c];
+    th[c] = __dadd_rn(cc, -__dmul_rn(__dadd_rn(cc, -x), d.z));   // no FMA contraction: reproducible on the host
+    m.prop[(size_t)i * ndim + c] = th[c];
+  }
+}
+
+// Large launches, before the setup: every walker's bucket key and the bucket histogram (MOVE: the proposals are
+// formed here, the setup then reads them from m.prop).
+template <bool MOVE>
+__global__ void __launch_bounds__(128) order_key_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k,
+                                                        const double* __restrict__ theta, const __grid_constant__ Move m) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool have = i < k.W;
+  double th[MP_MAX_NDIM];
+  int kk = -1;
+  if (have) {
+    if (MOVE) propose(m, i, p.ndim, th);
+    else
+      for (int c = 0; c < p.ndim; ++c) th[c] = theta[(size_t)i * p.ndim + c];
+    kk = order_key_of(p.sp, th);
+    k.key[i] = kk;
+  }
+  block_claim_by_key(have, kk, k.hist);
+  // the last block to get here turns the histogram into bucket offsets (saves a launch)
+  __shared__ int last;
+  __threadfence();
+  if (threadIdx.x == 0) last = atomicAdd(k.hist + kOrderBuckets + 2, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    scan_buckets<128>(k.hist);
+  }
+}
+
 // MOVE = false: walker i's parameters are theta[i][:].  MOVE = true: walker i is mover i of a stretch-move
-// half-step and its parameters are the proposal q, formed here and kept in m.prop for the accept step.
+// half-step and its parameters are the proposal q.  One thread per SLOT (= walker unless the launch is ordered).
 template <bool MOVE>
 __global__ void __launch_bounds__(128, 4) setup_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k,
                                                     const double* __restrict__ theta, const __grid_constant__ Move m) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool have = i < k.W;
+  const int sl = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool have = sl < k.W;
   const int ndim = p.ndim;
   double th[MP_MAX_NDIM];
   if (have) {
-    if (MOVE) {
-      const Draw d = draw_for(m, i);
-      const double* pc = m.coords;
-      if (m.n_peers > 0) {
-        // this mover's current row into the local replica (it is about to be moved here), the partner's from its home
-        const int hm = home_before_this_step(m, d.me);
-        if (hm != m.rank) {
-          const double* src = replica_coords(m, hm);
-          for (int c = 0; c < ndim; ++c) m.coords[(size_t)d.me * ndim + c] = src[(size_t)d.me * ndim + c];
-          m.lnp[d.me] = replica_lnp(m, hm)[d.me];
-        }
-        pc = replica_coords(m, m.split == 1 ? d.pj / m.n_mine : home_before_this_step(m, d.partner));
-      }
-      for (int c = 0; c < ndim; ++c) {
-        const double cc = pc[(size_t)d.partner * ndim + c];
-        const double x = m.coords[(size_t)d.me * ndim + c];
-        th[c] = __dadd_rn(cc, -__dmul_rn(__dadd_rn(cc, -x), d.z));   // no FMA contraction: reproducible on the host
-        m.prop[(size_t)i * ndim + c] = th[c];
-      }
+    const int i = k.slot_wid ? k.slot_wid[sl] : sl;
+    if (MOVE && !k.slot_wid) {
+      propose(m, i, ndim, th);
     } else {
-      for (int c = 0; c < ndim; ++c) th[c] = theta[(size_t)i * ndim + c];
+      const double* src = MOVE ? m.prop : theta;
+      for (int c = 0; c < ndim; ++c) th[c] = src[(size_t)i * ndim + c];
     }
   }
   bool to_explicit = false, to_implicit = false;
@@ -323,27 +365,21 @@ __global__ void __launch_bounds__(128, 4) setup_kernel(const __grid_constant__ P
     WalkerRec r;
     const double t_end = p.dv.n_nodes > 0 ? p.dv.node_t[p.dv.n_nodes - 1] : p.dv.t_start;
     prepare_walker(p.sp, th, ndim, p.prior_enabled != 0, p.lower, p.upper, p.dv.t_start, t_end, r);
-    if (!(r.status & kWalkerPriorReject)) rec_store(k, i, r);
+    if (!(r.status & kWalkerPriorReject)) rec_store(k, sl, r);
     y0 = r.y0; h0 = r.h0; n_rhs0 = r.n_rhs;
-    k.status[i] = r.status;
-    k.n_rhs[i] = r.n_rhs;
+    k.status[sl] = r.status;
+    k.n_rhs[sl] = r.n_rhs;
     // (a walker whose initialisation failed still goes to the integrator, which marks its nodes)
     const bool go = (r.status == kWalkerOk || r.status == kWalkerIntegratorFail) && p.dv.n_nodes > 0;
     to_implicit = go && p.sp.bucciantini && r.status == kWalkerOk;
     to_explicit = go && !to_implicit;
   }
-  if (k.key) {
-    const int kk = to_explicit ? order_key_of(p.sp, th) : -1;
-    if (have) k.key[i] = kk;
-    block_claim_by_key(to_explicit, kk, k.hist);
-  } else {
-    const int we = warp_append(to_explicit, k.counters + 0);
-    if (to_explicit) k.work[we] = i;
-  }
+  const int we = warp_append(to_explicit, k.counters + 0);      // (threads run in slot order: so does the work list)
+  if (to_explicit) k.work[we] = sl;
   const int wi = warp_append(to_implicit, k.counters + 2);
   if (to_implicit) {
     StiffRec q;
-    q.t = p.dv.t_start; q.y = y0; q.h = h0; q.wid = i; q.jn = 0; q.n_rhs = n_rhs0; q.n_steps = 0;
+    q.t = p.dv.t_start; q.y = y0; q.h = h0; q.wid = sl; q.jn = 0; q.n_rhs = n_rhs0; q.n_steps = 0;
     k.squeue[wi] = q;
   }
 }
@@ -502,9 +538,10 @@ struct Sink {
 };
 
 template <bool MOVE>
-__device__ __forceinline__ void deliver(const Problem& p, const Work& k, const Sink& s, const Move& m, int i, double lp_new,
+__device__ __forceinline__ void deliver(const Problem& p, const Work& k, const Sink& s, const Move& m, int sl, double lp_new,
                                         int st) {
-  const int nr = k.n_rhs[i];
+  const int nr = k.n_rhs[sl];
+  const int i = k.slot_wid ? k.slot_wid[sl] : sl;              // the walker this slot holds
   if (!MOVE) {
     s.lnp[i] = lp_new;
     if (s.status) s.status[i] = st;
@@ -547,19 +584,19 @@ __global__ void __launch_bounds__(64, 12) reduce_rows_kernel(const __grid_consta
   __shared__ double s_data[kDataSmemDoubles];
   DataView dv = p.dv;
   stage_data(p.dv, dv, s_data, 64);
-  const int i = blockIdx.x * 64 + threadIdx.x;
-  if (i >= k.W) return;
-  int st = k.status[i];
+  const int sl = blockIdx.x * 64 + threadIdx.x;
+  if (sl >= k.W) return;
+  int st = k.status[sl];
   double result = -INFINITY;
   if (!(st & kWalkerPriorReject)) {
     Walker w;
-    rec_load_lum(k, i, w);
-    double* o = (MODE == kModeModelAtData) ? out + (size_t)i * dv.n_data : nullptr;
-    const double chi2 = reduce_rows<MODE>(p.sp, dv, w, k.ybuf + (size_t)i * k.ws, o, nullptr, 1, p.dat_orig, k.ns);
+    rec_load_lum(k, sl, w);
+    double* o = (MODE == kModeModelAtData) ? out + (size_t)(k.slot_wid ? k.slot_wid[sl] : sl) * dv.n_data : nullptr;
+    const double chi2 = reduce_rows<MODE>(p.sp, dv, w, k.ybuf + (size_t)sl * k.ws, o, nullptr, 1, p.dat_orig, k.ns);
     if (MODE == kModeLnprob) result = lnlike_of(chi2, st);                       // + lnprior == 0.0
   }
-  if (MODE == kModeLnprob) deliver<MOVE>(p, k, s, m, i, result, st);
-  else if (s.status) s.status[i] = st;
+  if (MODE == kModeLnprob) deliver<MOVE>(p, k, s, m, sl, result, st);
+  else if (s.status) s.status[k.slot_wid ? k.slot_wid[sl] : sl] = st;
 }
 
 // One warp per walker, one DATUM per lane: the lane evaluates the luminosity stage at its datum's two
@@ -576,14 +613,15 @@ __global__ void __launch_bounds__(128) reduce_coop_kernel(const __grid_constant_
                                                           const __grid_constant__ Sink s, double* __restrict__ out,
                                                           const __grid_constant__ Move m) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * 128 + threadIdx.x) >> 5;
-  if (i >= k.W) return;
-  int st = k.status[i];
+  const int sl = (blockIdx.x * 128 + threadIdx.x) >> 5;
+  if (sl >= k.W) return;
+  const int i = k.slot_wid ? k.slot_wid[sl] : sl;              // the walker this slot holds
+  int st = k.status[sl];
   double chi2 = 0.0;
   if (!(st & kWalkerPriorReject)) {
     Walker w;
-    rec_load_lum(k, i, w);                                     // (every lane the same words: broadcast loads)
-    const double* row = k.ybuf + (size_t)i * k.ws;
+    rec_load_lum(k, sl, w);                                    // (every lane the same words: broadcast loads)
+    const double* row = k.ybuf + (size_t)sl * k.ws;
     const DataView& dv = p.dv;
     for (int d0 = 0; d0 < dv.n_data; d0 += 32) {
       const int d = d0 + lane;
@@ -620,7 +658,7 @@ __global__ void __launch_bounds__(128) reduce_coop_kernel(const __grid_constant_
   if (MODE == kModeLnprob) {
     double result = -INFINITY;
     if (!(st & kWalkerPriorReject)) result = lnlike_of(chi2, st);
-    deliver<MOVE>(p, k, s, m, i, result, st);
+    deliver<MOVE>(p, k, s, m, sl, result, st);
   } else if (s.status) {
     s.status[i] = st;
   }
@@ -632,12 +670,13 @@ __global__ void __launch_bounds__(128) reduce_curves_kernel(const __grid_constan
                                                             double* __restrict__ out, double* __restrict__ state,
                                                             int* __restrict__ status) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * 128 + threadIdx.x) >> 5;
-  if (i >= k.W) return;
+  const int sl = (blockIdx.x * 128 + threadIdx.x) >> 5;
+  if (sl >= k.W) return;
+  const int i = k.slot_wid ? k.slot_wid[sl] : sl;              // the walker this slot holds
   Walker w;
-  rec_load_lum(k, i, w);
+  rec_load_lum(k, sl, w);
   const int Nn = p.dv.n_nodes;
-  const double* row = k.ybuf + (size_t)i * k.ws;               // node-minor: k.ns == 1
+  const double* row = k.ybuf + (size_t)sl * k.ws;              // node-minor: k.ns == 1
   double* o = out + (size_t)i * 3 * Nn;
   double* so = state ? state + (size_t)i * 2 * Nn : nullptr;
   for (int j = lane; j < Nn; j += 32) {
@@ -651,7 +690,7 @@ __global__ void __launch_bounds__(128) reduce_curves_kernel(const __grid_constan
       so[Nn + j] = om;
     }
   }
-  if (lane == 0 && status) status[i] = k.status[i];
+  if (lane == 0 && status) status[i] = k.status[sl];
 }
 
 // Scatter of all-gathered packs (the collective exchange): packed row i of the half -> walker P(pos0 + i).
@@ -893,7 +932,8 @@ struct mp_handle {
     cudaStream_t stream = nullptr;
     unsigned long long* recs = nullptr;
     double* ybuf = nullptr;
-    int *status = nullptr, *n_rhs = nullptr, *work = nullptr, *counters = nullptr, *key = nullptr, *hist = nullptr;
+    int *status = nullptr, *n_rhs = nullptr, *work = nullptr, *counters = nullptr, *key = nullptr, *hist = nullptr,
+        *slot_wid = nullptr;
     StiffRec* squeue = nullptr;
     double* prop = nullptr;
     size_t cap_walkers = 0, cap_ybuf = 0, cap_prop = 0;
@@ -998,7 +1038,7 @@ extern "C" void mp_destroy(mp_handle* h) {
   cudaFree(h->s_status); cudaFree(h->s_nrhs); cudaFree(h->s_cstatus);
   auto free_lane = [](mp_handle::Lane& L) {
     cudaFree(L.recs); cudaFree(L.ybuf); cudaFree(L.status); cudaFree(L.n_rhs); cudaFree(L.work);
-    cudaFree(L.counters); cudaFree(L.squeue); cudaFree(L.prop); cudaFree(L.key); cudaFree(L.hist);
+    cudaFree(L.counters); cudaFree(L.squeue); cudaFree(L.prop); cudaFree(L.key); cudaFree(L.hist); cudaFree(L.slot_wid);
     if (L.stream) cudaStreamDestroy(L.stream);
   };
   for (auto& L : h->lanes) free_lane(L);
@@ -1064,18 +1104,19 @@ static int slab_walkers(int Nn) {
 static int ensure_work(mp_handle::Lane& L, int S, int Nn, int ndim_prop, Work& k) {
   int rc = MP_OK;
   if ((size_t)S > L.cap_walkers) {
-    cudaFree(L.recs); cudaFree(L.status); cudaFree(L.n_rhs); cudaFree(L.work); cudaFree(L.squeue); cudaFree(L.key);
-    L.recs = nullptr; L.status = L.n_rhs = L.work = L.key = nullptr; L.squeue = nullptr; L.cap_walkers = 0;
+    cudaFree(L.recs); cudaFree(L.status); cudaFree(L.n_rhs); cudaFree(L.work); cudaFree(L.squeue); cudaFree(L.key); cudaFree(L.slot_wid);
+    L.recs = nullptr; L.status = L.n_rhs = L.work = L.key = L.slot_wid = nullptr; L.squeue = nullptr; L.cap_walkers = 0;
     MP_CUDA(cudaMalloc((void**)&L.recs, (size_t)S * sizeof(WalkerRec)));      // kRecWords rows of S words
     MP_CUDA(cudaMalloc((void**)&L.status, (size_t)S * sizeof(int)));
     MP_CUDA(cudaMalloc((void**)&L.n_rhs, (size_t)S * sizeof(int)));
     MP_CUDA(cudaMalloc((void**)&L.work, (size_t)S * sizeof(int)));
     MP_CUDA(cudaMalloc((void**)&L.key, (size_t)S * sizeof(int)));
+    MP_CUDA(cudaMalloc((void**)&L.slot_wid, (size_t)S * sizeof(int)));
     MP_CUDA(cudaMalloc((void**)&L.squeue, (size_t)S * sizeof(StiffRec)));
     L.cap_walkers = (size_t)S;
   }
   if (!L.counters) MP_CUDA(cudaMalloc((void**)&L.counters, 4 * sizeof(int)));
-  if (!L.hist) MP_CUDA(cudaMalloc((void**)&L.hist, (kOrderBuckets + 1) * sizeof(int)));
+  if (!L.hist) MP_CUDA(cudaMalloc((void**)&L.hist, (kOrderBuckets + 3) * sizeof(int)));
   if ((rc = ensure(&L.ybuf, &L.cap_ybuf, (size_t)S * Nn))) return rc;
   if (ndim_prop > 0 && (rc = ensure(&L.prop, &L.cap_prop, (size_t)S * ndim_prop))) return rc;
   k.stride = (int)L.cap_walkers;
@@ -1122,14 +1163,17 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
     if (sk.n_rhs) sk.n_rhs += i0;
     MP_CUDA(cudaMemsetAsync(k.counters, 0, 4 * sizeof(int), stream));
     const bool ordered = n >= kOrderMinWalkers && Nn > 0;
-    k.key = ordered ? Lp->key : nullptr;
+    const double* th0 = MOVE ? nullptr : d_theta + (size_t)i0 * ndim;
+    k.key = Lp->key;
     k.hist = Lp->hist;
-    if (ordered) MP_CUDA(cudaMemsetAsync(k.hist, 0, (kOrderBuckets + 1) * sizeof(int), stream));
-    setup_kernel<MOVE><<<(n + 127) / 128, 128, 0, stream>>>(p, k, MOVE ? nullptr : d_theta + (size_t)i0 * ndim, ms);
+    k.slot_wid = ordered ? Lp->slot_wid : nullptr;
     if (ordered) {
-      order_scan_kernel<<<1, 1024, 0, stream>>>(k.hist, k.counters);
-      order_scatter_kernel<<<(n + 1023) / 1024, 1024, 0, stream>>>(n, k.key, k.hist, k.work, k.counters);
+      // slots in key order: keys + histogram (MOVE: and the proposals), scan, scatter -- then the setup runs per slot
+      MP_CUDA(cudaMemsetAsync(k.hist, 0, (kOrderBuckets + 3) * sizeof(int), stream));
+      order_key_kernel<MOVE><<<(n + 127) / 128, 128, 0, stream>>>(p, k, th0, ms);
+      order_scatter_kernel<<<(n + 1023) / 1024, 1024, 0, stream>>>(n, k.key, k.hist, k.slot_wid);
     }
+    setup_kernel<MOVE><<<(n + 127) / 128, 128, 0, stream>>>(p, k, th0, ms);
     // small launches: 32-thread blocks spread the warps over more SMs
     if (Nn == 0) {
       // (a handle without data -- lnprior-only callers: nothing to integrate, lnlike = -0.5 * 0)

@@ -29,6 +29,13 @@ for label, th in cases.items():
     if key == "mdr": th = th[np.lexsort((th[:, 3], np.round((th[:, 2] + th[:, 5]) * 4)))]
     md = th[:, 2] + th[:, 5]
     if key == "e_md": th = th[np.lexsort((md, np.round(th[:, 4] * 4)))]
+    if key == "e_mdD": th = th[np.lexsort((-md, np.round(th[:, 4] * 4)))]
+    if key == "eD_md": th = th[np.lexsort((md, -np.round(th[:, 4] * 4)))]
+    if key == "eD_mdD": th = th[np.lexsort((-md, -np.round(th[:, 4] * 4)))]
+    if key == "lpt": th = th[np.argsort(-(0.56 * th[:, 1] + 0.41 * th[:, 2] + 0.35 * th[:, 5] - 0.1 * th[:, 3]))]
+    if key == "e_lpt": th = th[np.lexsort((-(0.56 * th[:, 1] + 0.41 * th[:, 2] + 0.35 * th[:, 5]), np.round(th[:, 4] * 4)))]
+    if key == "e_mdZ":      # zig-zag: ascending in even bins, descending in odd ones
+        eb = np.round(th[:, 4] * 4); th = th[np.lexsort((np.where(eb % 2 == 0, md, -md), eb))]
     if key == "md_e": th = th[np.lexsort((th[:, 4], np.round(md * 4)))]
     if key == "e2_md": th = th[np.lexsort((md, np.round(th[:, 4] * 2)))]
     if key == "md2_e": th = th[np.lexsort((th[:, 4], np.round(md * 2)))]
