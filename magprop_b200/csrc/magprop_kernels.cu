@@ -1162,7 +1162,9 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
     if (sk.status) sk.status += i0;
     if (sk.n_rhs) sk.n_rhs += i0;
     MP_CUDA(cudaMemsetAsync(k.counters, 0, 4 * sizeof(int), stream));
-    const bool ordered = n >= kOrderMinWalkers && Nn > 0;
+    // (a sharded move that reads its rows from peer replicas forms its proposals inside the setup kernel, where the
+    // remote reads hide behind the other threads' arithmetic: in a kernel of their own they cost 0.07 ms per half-step)
+    const bool ordered = n >= kOrderMinWalkers && Nn > 0 && !(MOVE && m.n_peers > 0);
     const double* th0 = MOVE ? nullptr : d_theta + (size_t)i0 * ndim;
     k.key = Lp->key;
     k.hist = Lp->hist;
