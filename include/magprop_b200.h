@@ -261,6 +261,14 @@ int mp_chain_moments(const double* d_chain, int64_t n, int32_t ndim, double* mea
 int mp_chain_order_statistics(const double* d_chain, int64_t n, int32_t ndim, int32_t col,
                               const int64_t* ranks, int32_t n_ranks, double* values, int32_t device, void* stream);
 
+/* The comparison model of the reference's figure 5 (code/figure_5.py:222-363, "Ben's model": an accreting-mass
+ * magnetar with an exponentially draining disc, explicit Euler steps of 1 s in a Python loop over 1e6 elements).
+ * pars [W][6] physical (B, P, MdiscI, RdiscI, epsilon, delta; the last two are not used by this model);
+ * knobs [6] = alpha, cs7, k, omass, dipeff, propeff (figure_5.py:12,17-21); step i is at t = 1 + i s; every
+ * stride-th step is stored: out [W][3][ceil(n_steps/stride)] = Ltot, Lprop, Ldip (/1e50).  Host pointers.        */
+int mp_gompertz_curves(const double* pars, int32_t W, const double* knobs, int64_t n_steps, int32_t stride,
+                       double* out, int32_t device);
+
 /* Diagnostic: how many walkers of the most recent launch on this handle were bucketed as stiff
  * and re-run by the implicit (Radau IIA) launch.  Synchronises the device.               */
 int mp_last_stiff_count(mp_handle* h, int32_t* count);

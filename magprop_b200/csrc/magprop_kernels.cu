@@ -863,6 +863,76 @@ __global__ void rhs_kernel(double inertia_factor, double mdot_factor, double bre
   dydt[2 * i + 1] = (Nacc + Ndip) / inertia;
 }
 
+// ---- the comparison model of code/figure_5.py:222-363 ("Ben's model") --------------------------------------
+// An accreting-mass magnetar with an exponentially draining disc, advanced by explicit Euler steps of 1 s (the
+// reference: a Python loop over 1e6 array elements per parameter set).  One parameter set per thread, the script's
+// operation order kept (fractional powers through pow, as NumPy's **); every `stride`-th step is stored.
+// out [W][3][n_out] = Ltot, Lprop, Ldip in units of 1e50 erg/s (figure_5.py:354-368).
+__global__ void gompertz_kernel(const double* __restrict__ pars, int W, double alpha, double cs7, double k, double omass,
+                                double dipeff, double propeff, long long n_steps, int stride, long long n_out,
+                                double* __restrict__ out) {
+  const int wi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= W) return;
+  const double B = pars[6 * wi], P = pars[6 * wi + 1], MdiscI = pars[6 * wi + 2], RdiscI = pars[6 * wi + 3];
+  const double spin = P * 1.0e-3;                               // :224
+  const double Rdisc = RdiscI * 1.0e5;
+  const double visc = alpha * cs7 * 1.0e7 * Rdisc;
+  const double mu = 1.0e15 * B * (kR * kR * kR);
+  double omega = (2.0 * 3.141592653589793) / spin;             // :229
+  const double Mdisc0 = MdiscI * kMsol;
+  double M_bg = omass * kMsol;
+  const double Mdot0 = (3.0 * Mdisc0 * visc) / (Rdisc * Rdisc);  // :258
+  double Mdot = Mdot0, Msum = 0.0, tt = 1.0, omegadot = 0.0;
+  const double mu47 = pow(mu, 4.0 / 7.0), mu2 = mu * mu, c3 = kC * kC * kC, c2 = kC * kC, R2 = kR * kR, R3 = kR * kR * kR;
+  double* o = out + (size_t)wi * 3 * n_out;
+  for (long long i = 0; i < n_steps; ++i) {
+    if (i > 0) {                                                // :302-309
+      tt = tt + 1.0;
+      omega = omega + omegadot;
+      M_bg = M_bg + Msum;
+      Mdot = Mdot0 * exp((-3.0 * visc * tt) / (Rdisc * Rdisc));
+    }
+    const double GMb = kG * M_bg;
+    double Rm = mu47 * pow(GMb, -1.0 / 7.0) * pow(Mdot, -2.0 / 7.0);
+    const double Rc = pow(GMb / (omega * omega), 1.0 / 3.0);
+    const double light = kC / omega;
+    if (Rm >= (k * light)) Rm = k * light;
+    const double lr = light / Rm;
+    const double Ndip = (-2.0 / 3.0) * ((mu2 * (omega * omega * omega)) / c3) * (lr * lr * lr);
+    const double w = pow(Rm / Rc, 1.5);
+    const double nn = 1.0 - w;
+    const double inertia = 0.35 * M_bg * R2;
+    const double bigT = 0.5 * inertia * (omega * omega);
+    const double x = GMb / (kR * c2);
+    const double modW = 0.6 * M_bg * c2 * (x / (1.0 - 0.5 * x));
+    const double beta = bigT / modW;
+    double Nacc;
+    if (beta > 0.27) {
+      Nacc = 0.0;
+    } else if (Rm >= kR) {
+      Nacc = nn * sqrt(GMb * Rm) * Mdot;
+      if (!isfinite(Nacc)) Nacc = 0.0;
+    } else {
+      const double f = 1.0 - (omega / sqrt(GMb / R3));
+      Nacc = (i == 0) ? f / sqrt(GMb * kR) * Mdot : f * sqrt(GMb * kR) * Mdot;   // (:283-285 divides, :335-337 multiplies)
+      if (!isfinite(Nacc)) Nacc = 0.0;
+    }
+    if (Rc >= Rm) Msum = Mdot;                                  // :293-296, :341-344
+    else if (i == 0) Msum = 0.0;
+    omegadot = (Ndip + Nacc) / inertia;
+    if (i % stride == 0) {
+      double lp = (-1.0 * Nacc * omega) - ((GMb * Mdot) / Rm);
+      double ld = (mu2 * ((omega * omega) * (omega * omega))) / (6.0 * c3);
+      if (!isfinite(lp) || lp <= 0.0) lp = 0.0;                 // :354-361
+      if (!isfinite(ld) || ld <= 0.0) ld = 0.0;
+      const long long jo = i / stride;
+      o[jo] = ((propeff * lp) + (dipeff * ld)) * 1.0e-50;
+      o[n_out + jo] = lp * 1.0e-50;
+      o[2 * n_out + jo] = ld * 1.0e-50;
+    }
+  }
+}
+
 // ---- FP64 FMA peak: 8 independent chains per thread, 2 flop per DFMA ---------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
   double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -1654,6 +1724,29 @@ extern "C" int mp_chain_order_statistics(const double* d_chain, int64_t n, int32
   }
   cudaFree(d_hist);
   if (e != cudaSuccess) return fail(MP_ERR_CUDA, std::string("mp_chain_order_statistics: ") + cudaGetErrorString(e));
+  return MP_OK;
+}
+
+extern "C" int mp_gompertz_curves(const double* pars, int32_t W, const double* knobs, int64_t n_steps, int32_t stride,
+                                  double* out, int32_t device) {
+  if (!pars || !knobs || !out || W < 0 || n_steps < 1 || stride < 1) return fail(MP_ERR_BAD_ARG, "mp_gompertz_curves: bad argument");
+  if (W == 0) return MP_OK;
+  if (mp_device_count() <= device || device < 0)
+    return fail(MP_ERR_CUDA, "mp_gompertz_curves: no such CUDA device (magprop_b200 has no CPU path)");
+  MP_CUDA(cudaSetDevice(device));
+  const long long n_out = (n_steps + stride - 1) / stride;
+  double *d_p = nullptr, *d_o = nullptr;
+  MP_CUDA(cudaMalloc((void**)&d_p, (size_t)W * 6 * sizeof(double)));
+  cudaError_t e = cudaMalloc((void**)&d_o, (size_t)W * 3 * n_out * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(d_p, pars, (size_t)W * 6 * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    gompertz_kernel<<<(W + 31) / 32, 32>>>(d_p, W, knobs[0], knobs[1], knobs[2], knobs[3], knobs[4], knobs[5], n_steps, stride, n_out, d_o);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_o, (size_t)W * 3 * n_out * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d_p);
+  cudaFree(d_o);
+  if (e != cudaSuccess) return fail(MP_ERR_CUDA, std::string("mp_gompertz_curves: ") + cudaGetErrorString(e));
   return MP_OK;
 }
 

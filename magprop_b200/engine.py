@@ -191,3 +191,17 @@ def chain_order_statistics(d_chain: int, n: int, ndim: int, col: int, ranks, dev
     out = np.empty(ranks.size)
     A.check(lib.mp_chain_order_statistics(d_chain, n, ndim, col, A.ptr(ranks), ranks.size, A.ptr(out), device, stream or None))
     return out
+
+
+def gompertz_curves(pars, n_steps=10 ** 6, stride=1, alpha=0.1, cs7=1.0, k=0.9, omass=1.4, dipeff=1.0, propeff=1.0, device=0):
+    """The comparison model of the reference's figure 5 (``code/figure_5.py:222-363``) on the device:
+    returns ``(t, curves)`` with ``curves[W, 3, n_out]`` = Ltot, Lprop, Ldip (/1e50) at ``t = 1 + i*stride`` s."""
+    lib = A.load()
+    pars = np.atleast_2d(_f64(pars))
+    if pars.shape[1] != 6:
+        raise ValueError("pars must be [W, 6]")
+    knobs = np.array([alpha, cs7, k, omass, dipeff, propeff], dtype=np.float64)
+    n_out = (int(n_steps) + int(stride) - 1) // int(stride)
+    out = np.empty((pars.shape[0], 3, n_out), dtype=np.float64)
+    A.check(lib.mp_gompertz_curves(A.ptr(pars), pars.shape[0], A.ptr(knobs), int(n_steps), int(stride), A.ptr(out), device))
+    return 1.0 + np.arange(n_out, dtype=np.float64) * stride, out

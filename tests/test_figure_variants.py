@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import relerr
+from conftest import GOLDEN, relerr
 from magprop_b200 import _capi as A
 from oracle import magprop_oracle as O
 
@@ -100,3 +100,35 @@ def test_figure4_light_curves_vs_oracle(built):
         if idx[-1] != 10000:
             idx = np.r_[idx, 10000]
         assert_curves_close(out[0], tight[1:][:, idx])
+
+
+def test_gompertz_oracle_reproduces_the_reference_loop():
+    """The comparison model of figure 5 (figure_5.py:222-363): the oracle against vectors made by executing the
+    reference's own loop (oracle/make_goldens_gompertz.py)."""
+    from oracle import gompertz_oracle as GO
+    g = np.load(os.path.join(GOLDEN, "gompertz.npz"))
+    n = int(g["n_steps"])
+    for name, p in zip(g["names"], g["pars"]):
+        t, Ltot, Lp, Ld = GO.curves(p, n)
+        mine = np.array([t, Ltot, Lp, Ld])
+        assert np.array_equal(mine[:, ::20], g[f"{name}_curves"], equal_nan=True)
+        assert np.array_equal(mine[:, -1], g[f"{name}_last"], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_gompertz_comparator_on_the_device(built):
+    """The CUDA comparator against the reference loop's vectors (CUDA's pow/exp differ from libm by <= 2 ulp per call,
+    and the model is an explicit Euler recurrence: 1e-9 after 20 000 steps), its stride, and a full 1e6-step run."""
+    from magprop_b200.engine import gompertz_curves
+    g = np.load(os.path.join(GOLDEN, "gompertz.npz"))
+    n = int(g["n_steps"])
+    t, out = gompertz_curves(g["pars"], n_steps=n, stride=20)
+    for w, name in enumerate(g["names"]):
+        ref = g[f"{name}_curves"]
+        assert np.array_equal(t, ref[0])
+        assert relerr(out[w], ref[1:] / 1.0e50).max() < 1e-9
+    t1, full = gompertz_curves(g["pars"][:1], n_steps=2000, stride=1)
+    assert np.array_equal(full[0][:, ::20], gompertz_curves(g["pars"][:1], n_steps=2000, stride=20)[1][0])
+    tl, long_run = gompertz_curves(g["pars"], n_steps=10 ** 6, stride=1000)
+    assert long_run.shape == (4, 3, 1000) and np.isfinite(long_run).all() and tl[-1] == 999001.0
+    assert (long_run[:, 0] >= long_run[:, 1]).all() and (long_run[:, 0, -1] < long_run[:, 0, 0]).all()
