@@ -64,7 +64,12 @@ inline Spec make_spec(const mp_model_spec& m) {
   // that margin is spent on a 2x looser LOCAL tolerance, 4 rtol on y, calibrated on the 788 golden
   // walkers to give the same max / p99 / median lnprob error as plain stepping at rtol.
   s.rtol_y = 4.0 * s.rtol;
-  s.rtol_stiff = 0.0464 * std::pow(s.rtol, 2.0 / 3.0);
+  // The implicit variant's embedded estimate is O(h^4) for an O(h^6) error, so it is held to ~ rtol^(2/3), not rtol.
+  // The constant is calibrated on the golden walkers that reach the implicit integrator (114 of 775) and on 188 fresh
+  // draws from the stiff corner of the prior against the converged oracle: 0.0928 leaves their max / p99 lnprob error
+  // where 0.0464 had it (3.9e-8 / 3.6e-8 -- what the explicit phase before the hand-over contributes) at 17 % fewer
+  // implicit steps; 0.19 doubles it, 0.37 makes them the worst walkers of the set (3.1e-7).
+  s.rtol_stiff = 0.0928 * std::pow(s.rtol, 2.0 / 3.0);
   s.max_steps = (m.max_steps > 0) ? m.max_steps : 50000;
   return s;
 }
