@@ -60,6 +60,9 @@ def test_ensemble_order_is_a_keyed_permutation(hostsim):
             assert np.array_equal(np.sort(got), np.arange(n))
         hostsim.hs_ensemble_order(n, C.c_ulonglong(17), C.c_ulonglong(5), 0, got.ctypes.data_as(C.c_void_p))
         assert np.array_equal(got, np.arange(n))                       # randomize_split = 0: fixed halves
+    # the inverse (which rank moved a walker last, for the peer-read exchange): P^-1(P(g)) == g for every position
+    for n in (12, 50, 4096, 100000, 2097152):
+        assert hostsim.hs_ensemble_order_roundtrip(n, C.c_ulonglong(17), C.c_ulonglong(3)) == 0
     # over many steps every walker lands in half 0 about half of the time, and pairs decorrelate
     n = 64
     in0 = np.array([R.ensemble_order(n, 3, s)[: n // 2] for s in range(400)])

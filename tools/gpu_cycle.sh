@@ -13,5 +13,5 @@ for k,v in d["extra"].items(): print(" ",k,{a:(round(b,3) if isinstance(b,float)
 PY
 if [ "$2" = "full" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu > gpurun_out/ncu_l_$TAG.log 2>&1
-  ncu --set full --clock-control none --import-source on -k regex:eval_kernel -c 1 -s 3 -o gpurun_out/full_$TAG python bench.py --steps 1 --warmup 1 --no-extra --no-cpu --ensembles 1184 > gpurun_out/ncu_f_$TAG.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:advance_kernel -c 1 -s 2 -o gpurun_out/full_$TAG python bench.py --steps 1 --warmup 1 --no-extra --no-cpu > gpurun_out/ncu_f_$TAG.log 2>&1
 fi
