@@ -1007,6 +1007,8 @@ struct mp_handle {
     StiffRec* squeue = nullptr;
     double* prop = nullptr;
     size_t cap_walkers = 0, cap_ybuf = 0, cap_prop = 0;
+    int* hint_host = nullptr;    // pinned: 1 = the last ordered launch on this lane found a tight ensemble (see launch_eval)
+    unsigned since_check = 0;
   } lanes[2];
   std::map<cudaStream_t, Lane> user_lanes;
   std::mutex user_lanes_mu;
@@ -1107,6 +1109,7 @@ extern "C" void mp_destroy(mp_handle* h) {
   cudaFree(h->s_theta); cudaFree(h->s_out); cudaFree(h->s_state); cudaFree(h->s_lnp);
   cudaFree(h->s_status); cudaFree(h->s_nrhs); cudaFree(h->s_cstatus);
   auto free_lane = [](mp_handle::Lane& L) {
+    if (L.hint_host) cudaFreeHost(L.hint_host);
     cudaFree(L.recs); cudaFree(L.ybuf); cudaFree(L.status); cudaFree(L.n_rhs); cudaFree(L.work);
     cudaFree(L.counters); cudaFree(L.squeue); cudaFree(L.prop); cudaFree(L.key); cudaFree(L.hist); cudaFree(L.slot_wid);
     if (L.stream) cudaStreamDestroy(L.stream);
@@ -1187,6 +1190,7 @@ static int ensure_work(mp_handle::Lane& L, int S, int Nn, int ndim_prop, Work& k
   }
   if (!L.counters) MP_CUDA(cudaMalloc((void**)&L.counters, 4 * sizeof(int)));
   if (!L.hist) MP_CUDA(cudaMalloc((void**)&L.hist, (kOrderBuckets + 3) * sizeof(int)));
+  if (!L.hint_host && cudaMallocHost((void**)&L.hint_host, sizeof(int)) == cudaSuccess) *L.hint_host = 0;
   if ((rc = ensure(&L.ybuf, &L.cap_ybuf, (size_t)S * Nn))) return rc;
   if (ndim_prop > 0 && (rc = ensure(&L.prop, &L.cap_prop, (size_t)S * ndim_prop))) return rc;
   k.stride = (int)L.cap_walkers;
@@ -1234,7 +1238,12 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
     MP_CUDA(cudaMemsetAsync(k.counters, 0, 4 * sizeof(int), stream));
     // (a sharded move that reads its rows from peer replicas forms its proposals inside the setup kernel, where the
     // remote reads hide behind the other threads' arithmetic: in a kernel of their own they cost 0.07 ms per half-step)
-    const bool ordered = n >= kOrderMinWalkers && Nn > 0 && !(MOVE && m.n_peers > 0);
+    // A tight ensemble gains nothing from the ordering and pays two launches for it.  Whether an ensemble is tight is
+    // found on the device (order_key_kernel's scan); the flag travels to pinned host memory behind the launch and is read
+    // HERE, unsynchronised, by later launches on the same lane: after a tight launch the ordering is skipped, and re-tried
+    // every 16th launch.  Results do not depend on it (a walker's arithmetic is the same in any slot).
+    bool ordered = n >= kOrderMinWalkers && Nn > 0 && !(MOVE && m.n_peers > 0);
+    if (ordered && Lp->hint_host && *Lp->hint_host == 1 && (++Lp->since_check & 15) != 0) ordered = false;
     const double* th0 = MOVE ? nullptr : d_theta + (size_t)i0 * ndim;
     k.key = Lp->key;
     k.hist = Lp->hist;
@@ -1243,6 +1252,8 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
       // slots in key order: keys + histogram (MOVE: and the proposals), scan, scatter -- then the setup runs per slot
       MP_CUDA(cudaMemsetAsync(k.hist, 0, (kOrderBuckets + 3) * sizeof(int), stream));
       order_key_kernel<MOVE><<<(n + 127) / 128, 128, 0, stream>>>(p, k, th0, ms);
+      if (Lp->hint_host)
+        MP_CUDA(cudaMemcpyAsync(Lp->hint_host, k.hist + kOrderBuckets, sizeof(int), cudaMemcpyDeviceToHost, stream));
       order_scatter_kernel<<<(n + 1023) / 1024, 1024, 0, stream>>>(n, k.key, k.hist, k.slot_wid);
     }
     setup_kernel<MOVE><<<(n + 127) / 128, 128, 0, stream>>>(p, k, th0, ms);
