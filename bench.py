@@ -13,7 +13,7 @@ E = --ensembles per GPU (weak scaling: each rank owns its own ensembles, no
 data-path collective -- independent chains need none).
 
 Printed JSON (one line, rank 0): the contract of the task statement, plus
-  roofline      FP64 FMA roofline of eval_kernel (peak measured live by a DFMA
+  roofline      FP64 FMA roofline of the evaluation kernels (advance_kernel dominant; peak measured live by a DFMA
                 micro-benchmark on the same GPU; MEASURED_PEAKS.json has no FP64 entry)
   cpu_baseline  the oracle (CPU port of the reference's odeint path) timed on
                 this box's host cores on a bounded sample of the same workload
@@ -289,6 +289,7 @@ def run_ours(args):
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
+    launches0 = sum(lk.kernels_launched() for lk in liks.values())
     wall0 = time.perf_counter()
     for s in range(args.steps):
         flush.fill_(s & 0xFF)                       # L2 flush, outside the event pair
@@ -297,6 +298,7 @@ def run_ours(args):
         ev[s][1].record()
     barrier()
     wall = time.perf_counter() - wall0
+    gpu_launches = sum(lk.kernels_launched() for lk in liks.values()) - launches0
     clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -348,7 +350,7 @@ def run_ours(args):
                "sample": f"{n_cpu} lnprob evaluations of the same walker draws in {dt:.1f} s, multiprocessing.Pool({procs}); "
                          + cpu_description()}
 
-    # FP64 roofline of eval_kernel: executed flop (ncu-counted per RHS evaluation, RHS evaluations
+    # FP64 roofline of the evaluation kernels: executed flop (ncu-counted per RHS evaluation, RHS evaluations
     # counted live on the device) over the live-measured launch time, against the live DFMA peak.
     rhs_per_s = (value / world) * mean_nrhs
     stage_flop = NCU["stage_flop_per_eval"]["setup"] + NCU["stage_flop_per_eval"]["reduce"]
@@ -385,8 +387,9 @@ def run_ours(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * 6 * 8 * len(DATASETS),
                     "d2h_bytes_per_step": W * 8 * len(DATASETS)},
-            # per dataset per step: setup, work-list scan + scatter, advance (explicit), advance (implicit), reduce
-            "gpu_launches": 6 * args.steps * len(DATASETS),
+            # counted by the library: per dataset and step setup, advance (explicit), advance (implicit), reduce, plus the
+            # two work-list ordering kernels on the launches that order (the first, then every 16th on a tight ensemble)
+            "gpu_launches": gpu_launches,
             "clocks": clocks,
             "nonfinite_lnprob": bad,
             "wall_s_timed_region": wall,

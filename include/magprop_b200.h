@@ -273,6 +273,10 @@ int mp_gompertz_curves(const double* pars, int32_t W, const double* knobs, int64
  * and re-run by the implicit (Radau IIA) launch.  Synchronises the device.               */
 int mp_last_stiff_count(mp_handle* h, int32_t* count);
 
+/* Diagnostic: how many kernels of the evaluation pipeline (work-list ordering, setup, the two integrator launches,
+ * reduce) this handle has launched so far -- what bench.py reports as gpu_launches for its timed region.        */
+int64_t mp_kernels_launched(const mp_handle* h);
+
 /* FP64 FMA peak micro-benchmark (roofline denominator; MEASURED_PEAKS.json has
  * no FP64 entry): returns achieved TFLOP/s of dependent-chain-free DFMA.        */
 int mp_fp64_peak_tflops(int32_t device, double* tflops);

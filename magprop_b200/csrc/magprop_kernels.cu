@@ -1015,6 +1015,7 @@ struct mp_handle {
   int sm_count = 148;
   cudaStream_t stream = nullptr;   // == lanes[0].stream
   Lane* last_lane = nullptr;       // work space of the most recent launch (mp_last_stiff_count)
+  int64_t kernels_launched = 0;    // evaluation-pipeline kernels launched through this handle so far (mp_kernels_launched)
 };
 
 template <typename T>
@@ -1255,6 +1256,7 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
       if (Lp->hint_host)
         MP_CUDA(cudaMemcpyAsync(Lp->hint_host, k.hist + kOrderBuckets, sizeof(int), cudaMemcpyDeviceToHost, stream));
       order_scatter_kernel<<<(n + 1023) / 1024, 1024, 0, stream>>>(n, k.key, k.hist, k.slot_wid);
+      h->kernels_launched += 2;
     }
     setup_kernel<MOVE><<<(n + 127) / 128, 128, 0, stream>>>(p, k, th0, ms);
     // small launches: 32-thread blocks spread the warps over more SMs
@@ -1276,10 +1278,13 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
       else if (n <= kCoopSmallWalkers) reduce_coop_kernel<MODE, MOVE, true><<<(n + 3) / 4, 128, 0, stream>>>(p, k, sk, o, ms);
       else reduce_rows_kernel<MODE, MOVE><<<(n + 63) / 64, 64, 0, stream>>>(p, k, sk, o, ms);
     }
+    h->kernels_launched += (Nn == 0) ? 2 : 4;      // setup, advance (explicit), advance (implicit), reduce
     MP_CUDA(cudaGetLastError());
   }
   return MP_OK;
 }
+
+extern "C" int64_t mp_kernels_launched(const mp_handle* h) { return h ? h->kernels_launched : 0; }
 
 extern "C" int mp_lnprob_batch_device(mp_handle* h, const double* d_theta, int32_t W, int32_t ndim,
                                       double* d_lnp, int32_t* d_status, int32_t* d_n_rhs, void* stream) {

@@ -146,10 +146,14 @@ class Likelihood:
         return self.grid[idx]
 
     def last_stiff_count(self) -> int:
-        """Walkers of the last launch that were bucketed as stiff (synchronises)."""
+        """Walkers of the last launch that were handed to the implicit integrator (synchronises)."""
         n = C.c_int32(0)
         A.check(self._lib.mp_last_stiff_count(self._h, C.byref(n)))
         return n.value
+
+    def kernels_launched(self) -> int:
+        """Kernels of the evaluation pipeline launched through this handle so far."""
+        return int(self._lib.mp_kernels_launched(self._h))
 
     def stretch_half_step(self, d_coords, d_lnp, nwalkers, ndim, d_active, n_active, d_complement,
                           n_complement, a, seed, step, d_accepted=0, d_nrhs=0, stream=0):

@@ -1,7 +1,7 @@
 """NumPy restatement of the device stretch-move half-step (test double).
 
 Same counter-based RNG (Philox4x32-10, Salmon et al. 2011), same draw layout and
-the same arithmetic order as ``stretch_kernel`` in magprop_kernels.cu, with the
+the same arithmetic order as ``propose()`` and ``deliver()`` in magprop_kernels.cu, with the
 log-probability supplied by the caller.  Used (a) to check the kernel's RNG and
 accept/reject logic on the GPU and (b) as the CPU stand-in for the kernel in the
 gloo tests of the multi-rank driver."""

@@ -29,7 +29,7 @@ e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 nr = d_nr.cpu().numpy(); st = d_st.cpu().numpy()
 q = np.percentile(nr, [0, 25, 50, 75, 90, 99, 100]).astype(int)
-print("prior-uniform %s W=%d: %.3f ms  %.3e evals/s  stiff bucket %d  fails %d" % (name, W, ms, W / ms * 1e3, lk.last_stiff_count(), int(((st & 2) != 0).sum())))
+print("prior-uniform %s W=%d: %.3f ms  %.3e evals/s  stiff hand-overs %d  fails %d" % (name, W, ms, W / ms * 1e3, lk.last_stiff_count(), int(((st & 2) != 0).sum())))
 print("  n_rhs min/25/50/75/90/99/max", q.tolist(), "mean %.0f" % nr.mean(), " sum %.3e" % nr.sum())
 # per-warp imbalance of the explicit launch: max over the 32 lanes vs mean
 w = nr[: (W // 32) * 32].reshape(-1, 32)
