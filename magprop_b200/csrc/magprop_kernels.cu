@@ -65,7 +65,11 @@ struct Work {
   int* n_rhs;          // [W]
   int* work;           // [W] walkers for the explicit integrator
   StiffRec* squeue;    // [W] walkers for the implicit integrator
-  int* counters;       // [0] walkers in `work`, [1] next to hand out, [2] walkers in `squeue`, [3] next to hand out
+  int* counters;       // [0] walkers in `work`, [1] next to hand out, [2] walkers in `squeue`, [3] next to hand out,
+                       // [4..7] extent of the ensemble in the ordering's bins: max(im + 1), max(256 - im), max(ie + 1), max(32 - ie),
+                       // [8..11] the extent the host has been told
+  int track;           // 1: the setup kernel measures [4..7] (launches large enough to be ordered)
+  int* hint;           // (track) where the host reads [4..7] later: mapped pinned memory, written by the implicit launch's first thread
   // ordering of `work` (large launches): per-walker bucket key and the bucket histogram / cursors
   int* key;            // [W] bucket key of every walker
   int* hist;           // [kOrderBuckets + 3]: bucket counts / offsets, "tight" flag, tight cursor, block ticket
@@ -76,10 +80,12 @@ struct Work {
 // the same phases of the integration together only if their walkers are alike, so the walkers of a large launch are
 // given SLOTS -- the index under which all three stages keep a walker's record, node values and status, so that
 // neighbouring lanes also touch neighbouring memory -- in the order of a key of
-// the two parameter combinations that set a walker's timeline: the fallback time scale epsilon (quarter-decade
-// bins, ascending -- which also puts the long integrations first) and, within a bin, the mass that flows through
-// the disc, M_disc * delta (1/24-decade bins).  A counting sort: histogram in setup_kernel, one scan, one scatter.
-// Measured on 2^18 walkers against the unordered list: prior-uniform +16 %, posterior-like spreads +10..18 %,
+// the two parameter combinations that set a walker's timeline: the mass that flows through the disc, M_disc * delta
+// (1/24-decade bins, DESCENDING: the number of steps grows with it -- correlation 0.83..0.94 with log(steps) on
+// posterior-like ensembles of the four synthetic datasets -- and a launch whose long integrations start last ends
+// with a tail as long as one of them, `tools/sched_sim.py`) and, within a bin, the fallback time scale epsilon
+// (quarter-decade bins).  A counting sort: histogram in order_key_kernel, one scan, one scatter.
+// Measured on 2^18 walkers against the unordered list: prior-uniform +13 %, posterior-like spreads +10..30 %,
 // a 1e-4 ball unchanged; results do not depend on the order (tested).
 constexpr int kOrderBuckets = 32 * 256;
 #ifndef MP_ORDER_MIN_WALKERS
@@ -88,15 +94,23 @@ constexpr int kOrderBuckets = 32 * 256;
 constexpr int kOrderMinWalkers = MP_ORDER_MIN_WALKERS;
 constexpr int kCoopSmallWalkers = 2048;   // launches up to this size run stage 3 with a warp per walker (see reduce_coop_kernel)
 constexpr int kOrderTightBuckets = 8;
-__device__ __forceinline__ int order_key_of(const Spec& sp, const double* th) {
+__device__ __forceinline__ void order_bins(const Spec& sp, const double* th, int& ie, int& im) {
   const float le = ((sp.unlog_mask >> 4) & 1) ? (float)th[4] : __log10f((float)th[4]);
   const float lm = ((sp.unlog_mask >> 2) & 1) ? (float)th[2] : __log10f((float)th[2]);
   const float ld = ((sp.unlog_mask >> 5) & 1) ? (float)th[5] : __log10f((float)th[5]);
   const float eb = fminf(fmaxf((le + 4.0f) * 4.0f, 0.0f), 31.0f);
   const float mb = fminf(fmaxf((lm + ld + 10.0f) * 24.0f, 0.0f), 255.0f);
-  const int ie = (eb == eb) ? (int)eb : 0, im = (mb == mb) ? (int)mb : 0;
-  return ie * 256 + ((ie & 1) ? 255 - im : im);      // zig-zag: neighbouring buckets across an epsilon boundary are alike
+  ie = (eb == eb) ? (int)eb : 0;
+  im = (mb == mb) ? (int)mb : 0;
 }
+__device__ __forceinline__ int order_key_of(const Spec& sp, const double* th) {
+  int ie, im;
+  order_bins(sp, th, ie, im);
+  // descending in M*delta (the long integrations first), zig-zag in epsilon: neighbouring buckets across an M*delta boundary are alike
+  return (255 - im) * 32 + ((im & 1) ? 31 - ie : ie);
+}
+// An ensemble inside a few neighbouring buckets gains nothing from the ordering (launch_eval skips it).
+constexpr int kTightMdBins = 2, kTightEpsBins = 1;
 // The threads of a block claim slots of their keys' counters: lanes with the same key share one atomic, and when
 // the whole block holds one key (a tight ensemble: every walker in the same bucket) so do its warps -- otherwise
 // thousands of warps would queue on one address.  Every thread of the block must call (it synchronises).
@@ -374,6 +388,19 @@ __global__ void __launch_bounds__(128, 4) setup_kernel(const __grid_constant__ P
     to_implicit = go && p.sp.bucciantini && r.status == kWalkerOk;
     to_explicit = go && !to_implicit;
   }
+  if (k.track && (blockIdx.x & 15) == 0) {
+    // how far the ensemble reaches in the ordering's bins (the host decides from it whether the NEXT launch is
+    // ordered); every 16th block looks -- a sample of >= 512 walkers is ample for the purpose
+    const bool in = to_explicit || to_implicit;
+    int ie = 0, im = 0;
+    if (in) order_bins(p.sp, th, ie, im);
+    const int v[4] = {in ? im + 1 : 0, in ? 256 - im : 0, in ? ie + 1 : 0, in ? 32 - ie : 0};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int m = __reduce_max_sync(kFull, v[q]);
+      if ((threadIdx.x & 31) == 0 && m > __ldcg(k.counters + 4 + q)) atomicMax(k.counters + 4 + q, m);
+    }
+  }
   const int we = warp_append(to_explicit, k.counters + 0);      // (threads run in slot order: so does the work list)
   if (to_explicit) k.work[we] = sl;
   const int wi = warp_append(to_implicit, k.counters + 2);
@@ -416,6 +443,11 @@ advance_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k
     __syncthreads();
   }
   const int lane = threadIdx.x & 31;
+  if (STIFF && k.track && blockIdx.x == 0 && threadIdx.x == 0)        // (see launch_eval: the next launch's hint;
+    for (int q = 0; q < 4; ++q) {                                     // written over PCIe only when it changes)
+      const int v = k.counters[4 + q];
+      if (v != k.counters[8 + q]) { k.counters[8 + q] = v; k.hint[q] = v; }
+    }
   const int n_items = k.counters[STIFF ? 2 : 0];
   int* next = k.counters + (STIFF ? 3 : 1);
   const double t_end = ldd(node_t + (Nn - 1));
@@ -1007,8 +1039,8 @@ struct mp_handle {
     StiffRec* squeue = nullptr;
     double* prop = nullptr;
     size_t cap_walkers = 0, cap_ybuf = 0, cap_prop = 0;
-    int* hint_host = nullptr;    // pinned: 1 = the last ordered launch on this lane found a tight ensemble (see launch_eval)
-    unsigned since_check = 0;
+    int* hint_host = nullptr;    // mapped pinned int[4]: counters[4..7] of the last large launch on this lane (see launch_eval)
+    int* hint_dev = nullptr;     // the device's pointer to it
   } lanes[2];
   std::map<cudaStream_t, Lane> user_lanes;
   std::mutex user_lanes_mu;
@@ -1189,9 +1221,15 @@ static int ensure_work(mp_handle::Lane& L, int S, int Nn, int ndim_prop, Work& k
     MP_CUDA(cudaMalloc((void**)&L.squeue, (size_t)S * sizeof(StiffRec)));
     L.cap_walkers = (size_t)S;
   }
-  if (!L.counters) MP_CUDA(cudaMalloc((void**)&L.counters, 4 * sizeof(int)));
+  if (!L.counters) {             // [8..11]: what the host was told last (never reset)
+    MP_CUDA(cudaMalloc((void**)&L.counters, 12 * sizeof(int)));
+    MP_CUDA(cudaMemset(L.counters, 0, 12 * sizeof(int)));
+  }
   if (!L.hist) MP_CUDA(cudaMalloc((void**)&L.hist, (kOrderBuckets + 3) * sizeof(int)));
-  if (!L.hint_host && cudaMallocHost((void**)&L.hint_host, sizeof(int)) == cudaSuccess) *L.hint_host = 0;
+  if (!L.hint_host && cudaHostAlloc((void**)&L.hint_host, 4 * sizeof(int), cudaHostAllocMapped) == cudaSuccess) {
+    std::memset(L.hint_host, 0, 4 * sizeof(int));
+    if (cudaHostGetDevicePointer((void**)&L.hint_dev, L.hint_host, 0) != cudaSuccess) L.hint_dev = nullptr;
+  }
   if ((rc = ensure(&L.ybuf, &L.cap_ybuf, (size_t)S * Nn))) return rc;
   if (ndim_prop > 0 && (rc = ensure(&L.prop, &L.cap_prop, (size_t)S * ndim_prop))) return rc;
   k.stride = (int)L.cap_walkers;
@@ -1236,15 +1274,22 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
     if (sk.lnp) sk.lnp += i0;
     if (sk.status) sk.status += i0;
     if (sk.n_rhs) sk.n_rhs += i0;
-    MP_CUDA(cudaMemsetAsync(k.counters, 0, 4 * sizeof(int), stream));
+    MP_CUDA(cudaMemsetAsync(k.counters, 0, 8 * sizeof(int), stream));
     // (a sharded move that reads its rows from peer replicas forms its proposals inside the setup kernel, where the
     // remote reads hide behind the other threads' arithmetic: in a kernel of their own they cost 0.07 ms per half-step)
-    // A tight ensemble gains nothing from the ordering and pays two launches for it.  Whether an ensemble is tight is
-    // found on the device (order_key_kernel's scan); the flag travels to pinned host memory behind the launch and is read
-    // HERE, unsynchronised, by later launches on the same lane: after a tight launch the ordering is skipped, and re-tried
-    // every 16th launch.  Results do not depend on it (a walker's arithmetic is the same in any slot).
+    // A tight ensemble gains nothing from the ordering and pays two launches for it.  How far an ensemble reaches in the
+    // ordering's bins is measured by every large launch's setup kernel; the four numbers travel to pinned host memory
+    // behind the launch and are read HERE, unsynchronised, by the next launch on the same lane (a chain's ensemble moves
+    // slowly): inside kTightMdBins x kTightEpsBins the walkers are taken as they come.  Results do not depend on it (a
+    // walker's arithmetic is the same in any slot).
     bool ordered = n >= kOrderMinWalkers && Nn > 0 && !(MOVE && m.n_peers > 0);
-    if (ordered && Lp->hint_host && *Lp->hint_host == 1 && (++Lp->since_check & 15) != 0) ordered = false;
+    k.track = (ordered && Lp->hint_dev) ? 1 : 0;
+    k.hint = Lp->hint_dev;
+    if (ordered && Lp->hint_host) {
+      const volatile int* e = Lp->hint_host;
+      const int e0 = e[0], e1 = e[1], e2 = e[2], e3 = e[3];
+      if (e0 > 0 && e0 + e1 - 257 <= kTightMdBins && e2 + e3 - 33 <= kTightEpsBins) ordered = false;
+    }
     const double* th0 = MOVE ? nullptr : d_theta + (size_t)i0 * ndim;
     k.key = Lp->key;
     k.hist = Lp->hist;
@@ -1253,8 +1298,6 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
       // slots in key order: keys + histogram (MOVE: and the proposals), scan, scatter -- then the setup runs per slot
       MP_CUDA(cudaMemsetAsync(k.hist, 0, (kOrderBuckets + 3) * sizeof(int), stream));
       order_key_kernel<MOVE><<<(n + 127) / 128, 128, 0, stream>>>(p, k, th0, ms);
-      if (Lp->hint_host)
-        MP_CUDA(cudaMemcpyAsync(Lp->hint_host, k.hist + kOrderBuckets, sizeof(int), cudaMemcpyDeviceToHost, stream));
       order_scatter_kernel<<<(n + 1023) / 1024, 1024, 0, stream>>>(n, k.key, k.hist, k.slot_wid);
       h->kernels_launched += 2;
     }
