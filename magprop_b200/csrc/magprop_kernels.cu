@@ -426,13 +426,19 @@ __global__ void __launch_bounds__(128, 4) setup_kernel(const __grid_constant__ P
 #ifndef MP_MIN_BLOCKS_64
 #define MP_MIN_BLOCKS_64 10
 #endif
+// Resident warps per SM the implicit variant is compiled for: 12 (166 registers, no spills), and 16 (128 registers)
+// for launches large enough that its queue is longer than one wave of the 12-warp build -- 75 904 stiff walkers of
+// 2^18 prior-uniform ones on 56 832 lanes are 1.34 waves, on 75 776 lanes one: 7.13 -> 6.71 ms per launch, 10^6
+// walkers 22.2 -> 21.5; a single wave (2^16 walkers) is faster on the 12-warp build, 4.78 against 5.19 ms.
 #ifndef MP_STIFF_MIN_WARPS
-#define MP_STIFF_MIN_WARPS 12     // resident warps per SM the implicit variant is compiled for
+#define MP_STIFF_MIN_WARPS 12
 #endif
+constexpr int kStiffWarpsWide = 16;
+constexpr int kStiffWideMinWalkers = 196608;
 constexpr int kNodeSmemDoubles = 512;      // node times staged per block when they fit (4 KB)
 
-template <bool STIFF, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, STIFF ? (MP_STIFF_MIN_WARPS * 32 / BLOCK) : (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64))
+template <bool STIFF, int BLOCK, int STIFF_WARPS = MP_STIFF_MIN_WARPS>
+__global__ void __launch_bounds__(BLOCK, STIFF ? (STIFF_WARPS * 32 / BLOCK) : (BLOCK == 32 ? MP_MIN_BLOCKS_32 : MP_MIN_BLOCKS_64))
 advance_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k) {
   __shared__ double s_nodes[kNodeSmemDoubles];
   const int Nn = p.dv.n_nodes;
@@ -467,7 +473,7 @@ advance_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k
     // is not -- prior-uniform, where the step counts differ tenfold -- the wait is over after MP_REFILL_PATIENCE trips.
     const unsigned idle = __ballot_sync(kFull, !have);
 #ifndef MP_REFILL_PATIENCE
-#define MP_REFILL_PATIENCE 16
+#define MP_REFILL_PATIENCE 32
 #endif
     waited = idle ? waited + 1 : 0;
     if (idle && !empty && (idle == kFull || waited > MP_REFILL_PATIENCE)) {
@@ -1310,7 +1316,10 @@ static int launch_eval(mp_handle* h, const Problem& p, const double* d_theta, in
       advance_kernel<true, 32><<<std::min((n + 31) / 32, h->sm_count * MP_STIFF_MIN_WARPS), 32, 0, stream>>>(p, k);
     } else {
       advance_kernel<false, 64><<<std::min((n + 63) / 64, h->sm_count * MP_MIN_BLOCKS_64), 64, 0, stream>>>(p, k);
-      advance_kernel<true, 64><<<std::min((n + 63) / 64, h->sm_count * MP_STIFF_MIN_WARPS / 2), 64, 0, stream>>>(p, k);
+      if (n >= kStiffWideMinWalkers)
+        advance_kernel<true, 64, kStiffWarpsWide><<<std::min((n + 63) / 64, h->sm_count * kStiffWarpsWide / 2), 64, 0, stream>>>(p, k);
+      else
+        advance_kernel<true, 64><<<std::min((n + 63) / 64, h->sm_count * MP_STIFF_MIN_WARPS / 2), 64, 0, stream>>>(p, k);
     }
     if (MODE == kModeCurves) {
       reduce_curves_kernel<<<(n + 3) / 4, 128, 0, stream>>>(p, k, out + (size_t)i0 * 3 * Nn,
