@@ -28,14 +28,14 @@
 
 #if defined(__CUDACC__)
 #define MP_HD __host__ __device__ __forceinline__
-#define MP_TABLE_QUALIFIER __device__ const __align__(16)
+#define MP_TABLE_QUALIFIER __device__ const __align__(128)
 // NOT const on the device: a const __constant__ array with a visible initialiser is folded into
 // immediates, and every FP64 immediate costs two extra MOVs; a mutable one stays a c[3][..] operand.
 #define MP_CONST_QUALIFIER __constant__
 #else
 #define MP_CONST_QUALIFIER static const
 #define MP_HD inline
-#define MP_TABLE_QUALIFIER alignas(16) static const
+#define MP_TABLE_QUALIFIER alignas(128) static const
 #endif
 
 #include "disc_table.inc"
@@ -162,6 +162,20 @@ MP_HD bool table_locate_safe(double u, TableAt& ta) {
 }
 MP_HD bool table_locate(double u, TableAt& ta) { return table_locate_safe(u, ta); }
 
+// The same for the explicit integrator's table (mp_disc_fast: S alone, degree 6, 32 sub-intervals per binade).
+MP_HD bool table_locate_fast(double u, TableAt& ta) {
+  const int hi = dhi(u);
+  const int sh = 20 - MP_DISC_FAST_NSUB_LOG2;
+  const unsigned idx = (unsigned)((hi >> sh) - ((1023 + MP_DISC_EMIN) << MP_DISC_FAST_NSUB_LOG2));
+  const bool in = idx < (unsigned)((MP_DISC_EMAX - MP_DISC_EMIN + 1) << MP_DISC_FAST_NSUB_LOG2);
+  ta.row = &mp_disc_fast[in ? idx : 0u][0];
+  const unsigned uh = (unsigned)hi;
+  const double centre = dfromhi((uh & ~((1u << sh) - 1u)) | (1u << (sh - 1)));
+  const double scale = dfromhi(((unsigned)(2046 + MP_DISC_FAST_NSUB_LOG2 + 1) << 20) - (uh & 0x7ff00000u));
+  ta.s = (u - centre) * scale;
+  return in;
+}
+
 // degree-10 polynomial, split into even/odd halves for ILP
 MP_HD double poly10(const double* c, double s) {
   const double s2 = s * s;
@@ -198,6 +212,18 @@ MP_HD double poly10p(const double* c, double s, double s2) {
   od = fma(od, s2, p3.y);
   ev = fma(ev, s2, p3.x);
   od = fma(od, s2, p2.y);
+  ev = fma(ev, s2, p2.x);
+  od = fma(od, s2, p1.y);
+  ev = fma(ev, s2, p1.x);
+  od = fma(od, s2, p0.y);
+  ev = fma(ev, s2, p0.x);
+  return fma(od, s, ev);
+}
+
+// degree 6 on a row of mp_disc_fast: (c0,c1) (c2,c3) (c4,c5) (c6,pad), 64 bytes = half a cache line.
+MP_HD double poly6p(const double* c, double s, double s2) {
+  const Pair p3 = ld2(c + 6), p2 = ld2(c + 4), p1 = ld2(c + 2), p0 = ld2(c);
+  double ev = p3.x, od = p2.y;
   ev = fma(ev, s2, p2.x);
   od = fma(od, s2, p1.y);
   ev = fma(ev, s2, p1.x);
@@ -1226,7 +1252,7 @@ MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, do
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     u[s] = fma(ts[s], w.inv_tv, w.eps);
-    in_all = table_locate_safe(u[s], ta[s]) && in_all;
+    in_all = table_locate_fast(u[s], ta[s]) && in_all;
   }
   if (!in_all) {                                        // parameters far outside the prior box
     disc_stages<5>(w, ts, d);
@@ -1241,7 +1267,7 @@ MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, do
   const double E[5] = {Et * a18, Et * a27, Et * a72, Et * (a72 * a8), Et * (a72 * a18)};
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
-    const double S = poly10p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
+    const double S = poly6p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
     const double M = fma(w.K, S, E[s]);
     d[s].ni = M * w.g_tvI;
     d[s].qa = w.g_sqrtA * pow_m17_seeded1(M);
