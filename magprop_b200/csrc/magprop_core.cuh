@@ -162,7 +162,7 @@ MP_HD bool table_locate_safe(double u, TableAt& ta) {
 }
 MP_HD bool table_locate(double u, TableAt& ta) { return table_locate_safe(u, ta); }
 
-// The same for the explicit integrator's table (mp_disc_fast: S alone, degree 6, 32 sub-intervals per binade).
+// The same for the explicit integrator's table (mp_disc_fast: S alone, lower degree on more sub-intervals per binade).
 MP_HD bool table_locate_fast(double u, TableAt& ta) {
   const int hi = dhi(u);
   const int sh = 20 - MP_DISC_FAST_NSUB_LOG2;
@@ -220,8 +220,9 @@ MP_HD double poly10p(const double* c, double s, double s2) {
   return fma(od, s, ev);
 }
 
-// degree 6 on a row of mp_disc_fast: (c0,c1) (c2,c3) (c4,c5) (c6,pad), 64 bytes = half a cache line.
-MP_HD double poly6p(const double* c, double s, double s2) {
+// A row of mp_disc_fast (degree MP_DISC_FAST_DEG, see tools/gen_disc_table.py).
+MP_HD double polyfast(const double* c, double s, double s2) {
+#if MP_DISC_FAST_DEG == 6
   const Pair p3 = ld2(c + 6), p2 = ld2(c + 4), p1 = ld2(c + 2), p0 = ld2(c);
   double ev = p3.x, od = p2.y;
   ev = fma(ev, s2, p2.x);
@@ -230,6 +231,17 @@ MP_HD double poly6p(const double* c, double s, double s2) {
   od = fma(od, s2, p0.y);
   ev = fma(ev, s2, p0.x);
   return fma(od, s, ev);
+#elif MP_DISC_FAST_DEG == 5      // (c0,c1) (c2,c3) (c4,c5): 48-byte rows
+  const Pair p2 = ld2(c + 4), p1 = ld2(c + 2), p0 = ld2(c);
+  double ev = p2.x, od = p2.y;
+  ev = fma(ev, s2, p1.x);
+  od = fma(od, s2, p1.y);
+  ev = fma(ev, s2, p0.x);
+  od = fma(od, s2, p0.y);
+  return fma(od, s, ev);
+#else
+#error "mp_disc_fast: degree 5 or 6"
+#endif
 }
 
 // S outside the table (rare): convergent series below 2^-10, asymptotic above 2^22.
@@ -1267,7 +1279,7 @@ MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, do
   const double E[5] = {Et * a18, Et * a27, Et * a72, Et * (a72 * a8), Et * (a72 * a18)};
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
-    const double S = poly6p(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
+    const double S = polyfast(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
     const double M = fma(w.K, S, E[s]);
     d[s].ni = M * w.g_tvI;
     d[s].qa = w.g_sqrtA * pow_m17_seeded1(M);

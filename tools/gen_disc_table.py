@@ -30,12 +30,14 @@ EMIN, EMAX = -10, 21
 NSUB = 8
 DEG = 10
 ROW = 12  # padded row length (doubles)
-# The explicit integrator's own, denser table of S alone: degree 6 on 32 sub-intervals per binade -- 64-byte rows
-# (four 16-byte loads, six FMAs per lookup instead of six loads and ten FMAs); 3.4e-14 of the interval's max |S|,
-# four orders below the step tolerance it feeds.
-FAST_NSUB = 32
-FAST_DEG = 6
-FAST_ROW = 8
+# The explicit integrator's own, denser table of S alone: degree 5 on 64 sub-intervals per binade -- 48-byte rows
+# (three 16-byte loads, five FMAs per lookup instead of six loads and ten FMAs); 5.9e-14 of the interval's max |S|,
+# four orders below the step tolerance it feeds.  (Degree 6 on 32 sub-intervals, 64-byte rows, 3.4e-14: 1 % faster
+# on an ensemble whose lanes all read the same row, 3-6 % slower on spread-out ones, where every lane's row is
+# another L1 wavefront -- measured.)
+FAST_NSUB = 64
+FAST_DEG = 5
+FAST_ROW = 6
 
 
 def S(u):

@@ -26,12 +26,12 @@ for wi, ti, f, ln, src in sorted(lines, reverse=True)[:top]:
     print(f"{100 * wi / tot_w:5.1f}%  {wi:>12,}  thr {ti / wi:5.1f}  {f}:{ln}  {src[:110]}")
 
 # ---- by region of magprop_core.cuh (line ranges of the functions on the integrator's path)
-REGIONS = [("bits/table_locate/poly10p/ld2", 108, 207), ("exp_c", 287, 313), ("pow_m17_fast/cold", 315, 361), ("pow_m17_seeded(1)", 362, 412),
-           ("rsqrt_pos(2)/rcp_pos", 630, 670), ("exp_small", 671, 694), ("exp_small10+rcp_pos2", 695, 725), ("spin_g", 764, 824),
-           ("dense_eval", 849, 860), ("controller", 944, 960), ("breakup_sliding", 988, 1022), ("locate_kink", 1023, 1065),
-           ("step_spin_chain", 1066, 1170), ("disc_stages<N>", 1171, 1212), ("disc_stages_dp5", 1213, 1251),
-           ("integrator_step", 1252, 1290), ("spin_fJ", 1300, 1350), ("radau_step", 1351, 1480), ("load/drain_nodes", 1580, 1629),
-           ("luminosity stage", 570, 629)]
+REGIONS = [("bits/table_locate/poly/ld2", 108, 233), ("exp_c", 313, 339), ("pow_m17_fast/cold", 341, 387), ("pow_m17_seeded(1)", 388, 438),
+           ("rsqrt_pos(2)/rcp_pos", 656, 696), ("exp_small", 697, 720), ("exp_small10+rcp_pos2", 721, 751), ("spin_g", 790, 850),
+           ("dense_eval", 875, 886), ("controller", 970, 986), ("breakup_sliding", 1014, 1048), ("locate_kink", 1049, 1091),
+           ("step_spin_chain", 1092, 1196), ("disc_stages<N>", 1197, 1238), ("disc_stages_dp5", 1239, 1277),
+           ("integrator_step", 1278, 1316), ("spin_fJ", 1326, 1376), ("radau_step", 1377, 1506), ("load/drain_nodes", 1606, 1655),
+           ("luminosity stage", 596, 655)]
 agg = collections.OrderedDict((n, [0, 0]) for n, _, _ in REGIONS)
 other = collections.Counter(); other_t = collections.Counter()
 for wi, ti, f, ln, src in lines:
