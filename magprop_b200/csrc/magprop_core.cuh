@@ -446,6 +446,31 @@ MP_HD double pow_m17_seeded1(double x) {
   return fma(y * (1.0 / 7.0), e, y);
 }
 
+// The two halves of pow_m17_seeded1 for a block of independent evaluations: the range test of every
+// argument first, then the straight-line seeded power -- no branch between the chains, so the compiler
+// can interleave them.
+MP_HD bool pow_m17_seedable(double x) {
+  const unsigned hi = (unsigned)(dbits(x) >> 32);
+  return hi - (897u << 20) < (253u << 20);
+}
+MP_HD double pow_m17_seeded1_inrange(double x) {
+#if defined(__CUDA_ARCH__) && !defined(MP_POW_CVT)
+  const long long xb = __double_as_longlong(x);
+  const unsigned hi = (unsigned)(xb >> 32), lo = (unsigned)xb;
+  const float xf = __uint_as_float(((hi - (896u << 20)) << 3) | (lo >> 29));
+  float lg, sf;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(lg * (-1.0f / 7.0f)));
+  const unsigned fb = __float_as_uint(sf);
+  const double y = __hiloint2double((int)((fb >> 3) + (896u << 20)), (int)(fb << 29));
+  const double y2 = y * y, y4 = y2 * y2;
+  const double e = fma(-x, (y4 * y2) * y, 1.0);
+  return fma(y * (1.0 / 7.0), e, y);
+#else
+  return pow_m17_seeded1(x);
+#endif
+}
+
 MP_HD double rcp_fast(double x) {
 #if defined(__CUDA_ARCH__)
   return __drcp_rn(x);
@@ -860,13 +885,52 @@ MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double 
   return spin_g(sp, w, d, y, side, regime);
 }
 
+// Step-size control: Hairer's dopri5 PI controller (beta = 0.04, safety 0.9; h may shrink 5x, grow 10x),
+//   accepted:  h_new = h / clamp(err^(0.2 - 0.75 beta) / facold^beta / safety, 0.1, 5),  facold <- max(err, 1e-4)
+//   rejected:  h_new = h / min(err^(0.2 - 0.75 beta) / safety, 5)
+// evaluated in the log2 domain, in single precision (it steers the step size only): err = aerr/sk becomes a
+// difference of two logarithms, the divisions become subtractions, the clamps stay clamps, and one exp2 gives
+// 1/fac -- no IEEE division, none of the range checks and fix-up branches of logf/exp2f/"/" on the step's
+// serial tail (measured: +2 % with approximate reciprocals alone).  `lfacold` is log2(facold).
+struct StepControl {
+  static constexpr float beta = 0.04f, expo1 = 0.2f - 0.04f * 0.75f;
+  static constexpr float l_safe = -0.15200309f;      // log2(0.9)
+  static constexpr float l_shrink = 2.3219281f;      // log2(5)
+  static constexpr float l_grow = -3.3219281f;       // log2(0.1)
+  static constexpr float l_err_min = -99.657843f;    // log2(1e-30)
+  static constexpr float l_err_nan = 33.219281f;     // log2(1e10): NaN => shrink hard
+  static constexpr float l_facold_min = -13.287712f; // log2(1e-4)
+};
+MP_HD float log2_error_ratio(double aerr, double sk) {
+  float l;
+#if defined(__CUDA_ARCH__)
+  float la, ls;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(la) : "f"((float)aerr));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(ls) : "f"((float)sk));
+  l = la - ls;
+#else
+  l = log2f((float)aerr) - log2f((float)sk);
+#endif
+  if (!(l == l)) l = StepControl::l_err_nan;
+  return fmaxf(l, StepControl::l_err_min);
+}
+MP_HD double step_scale(float minus_log2_fac) {     // 1/fac
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(minus_log2_fac));
+  return (double)r;
+#else
+  return (double)exp2f(minus_log2_fac);
+#endif
+}
+
 // ---- Dormand-Prince 5(4) with dense output --------------------------------
 // Coefficients: Dormand & Prince 1980; dense output: Hairer, Norsett & Wanner II.6.
 // State of the spin integration of one walker.
 // The state variable `omega` holds omega in the implicit variant and y = omega^-2 in the explicit one.
 struct Integrator {
   double t, omega, h, k1;        // k1 = f(t, state) (FSAL)
-  float facold;
+  float lfacold;                 // log2 of the controller's previous error ratio (see StepControl)
   int rejected;                  // previous attempt was rejected
   // dense output of the last accepted step: omega(t0 + theta*hs)
   double t0, hs, r1, r2, r3, r4, r5;   // covers [t0, t]
@@ -928,7 +992,7 @@ MP_HD void integrator_init(const Spec& sp, const Walker& w, double t_start, doub
                            Integrator& in) {
   in.t = t_start;
   in.omega = INVSQ ? 1.0 / (w.omega0 * w.omega0) : w.omega0;
-  in.facold = 1.0e-4f;
+  in.lfacold = StepControl::l_facold_min;
   in.rejected = 0;
   in.n_steps = 0;
   in.stiff = 0;
@@ -967,7 +1031,7 @@ MP_HD void integrator_resume(double t, double omega, double h, Integrator& in) {
   in.omega = omega;
   in.h = h;
   in.k1 = 0.0;
-  in.facold = 1.0e-4f;
+  in.lfacold = StepControl::l_facold_min;
   in.rejected = 0;
   in.n_rhs = 0; in.n_steps = 0;
   in.stiff = 0; in.stiff_votes = 0;
@@ -977,22 +1041,6 @@ MP_HD void integrator_resume(double t, double omega, double h, Integrator& in) {
   in.status = (omega == omega && h > 0.0) ? kWalkerOk : kWalkerIntegratorFail;
   in.t0 = t; in.hs = 1.0;
   in.r1 = omega; in.r2 = in.r3 = in.r4 = in.r5 = 0.0;
-}
-
-// Step-size factors of the PI controller (Hairer's dopri5: beta = 0.04, safety 0.9).
-// They steer the step size only, so single precision is ample:
-//   fac11 = err^(0.2 - 0.75 beta),  fac = fac11 / facold^beta
-MP_HD void controller(float err, float facold, float& fac11, float& fac) {
-  const float beta = 0.04f, expo1 = 0.2f - beta * 0.75f;
-#if defined(__CUDA_ARCH__)
-  const float l = __log2f(fmaxf(err, 1.0e-30f));
-  fac11 = exp2f(expo1 * l);
-  fac = exp2f(expo1 * l - beta * __log2f(facold));
-#else
-  const float l = log2f(fmaxf(err, 1.0e-30f));
-  fac11 = exp2f(expo1 * l);
-  fac = exp2f(expo1 * l - beta * log2f(facold));
-#endif
 }
 
 // Dormand-Prince tableau (classic form) for the block step, as constant-bank operands.
@@ -1137,15 +1185,11 @@ MP_HD int step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, const
   const double sk = sp.rtol_y * fmax(fabs(y), fabs(ynew));
   const double aerr = fabs(errv);
   const bool accept = aerr <= sk;                 // false for NaN
-  float errf = (float)aerr / (float)sk;
-  if (!(errf == errf)) errf = 1.0e10f;            // NaN => shrink hard
-  float fac11, fac;
-  controller(errf, in.facold, fac11, fac);
-  const float safe = 0.9f, facc1 = 5.0f, facc2 = 0.1f;   // h may shrink 5x, grow 10x
+  const float lerr = log2_error_ratio(aerr, sk);
   if (accept) {
-    fac = fmaxf(facc2, fminf(facc1, fac / safe));
-    const double hnew = h * (double)(1.0f / fac);
-    in.facold = fmaxf(errf, 1.0e-4f);
+    const float g = StepControl::expo1 * lerr - StepControl::beta * in.lfacold - StepControl::l_safe;   // log2(fac)
+    const double hnew = h * step_scale(-fmaxf(StepControl::l_grow, fminf(StepControl::l_shrink, g)));
+    in.lfacold = fmaxf(lerr, StepControl::l_facold_min);
     // dense output (Hairer's contd5)
     const double dsum = fma(DP::d7(), k7, fma(DP::d6(), k6, fma(DP::d5(), k5, fma(DP::d4(), k4, fma(DP::d3(), k3, DP::d1() * k1)))));
     const double ydiff = ynew - y;
@@ -1194,7 +1238,7 @@ MP_HD int step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, const
     return 1;
   }
   // rejected
-  const double hnew = h * (double)(1.0f / fminf(facc1, fac11 / safe));
+  const double hnew = h * step_scale(-fminf(StepControl::l_shrink, StepControl::expo1 * lerr - StepControl::l_safe));
   in.h = hnew;
   in.h_resume = 0.0;                  // (a rejected landing attempt: the shorter retry no longer reaches the kink)
   in.rejected = 1;
@@ -1277,12 +1321,28 @@ MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, do
   const double a2 = a * a, a4 = a2 * a2, a8 = a4 * a4, a9 = a8 * a;
   const double a18 = a9 * a9, a27 = a18 * a9, a36 = a18 * a18, a72 = a36 * a36;
   const double E[5] = {Et * a18, Et * a27, Et * a72, Et * (a72 * a8), Et * (a72 * a18)};
+  // The seeded power's range test is taken once for the five arguments (not once per stage: a branch between
+  // the stages keeps the compiler from interleaving their chains -- measured +4 % on the headline workload).
+  double M[5];
+  bool seedable = true;
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     const double S = polyfast(ta[s].row, ta[s].s, ta[s].s * ta[s].s);
-    const double M = fma(w.K, S, E[s]);
-    d[s].ni = M * w.g_tvI;
-    d[s].qa = w.g_sqrtA * pow_m17_seeded1(M);
+    M[s] = fma(w.K, S, E[s]);
+    seedable = pow_m17_seedable(M[s]) && seedable;
+  }
+  if (seedable) {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      d[s].ni = M[s] * w.g_tvI;
+      d[s].qa = w.g_sqrtA * pow_m17_seeded1_inrange(M[s]);
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+      d[s].ni = M[s] * w.g_tvI;
+      d[s].qa = w.g_sqrtA * pow_m17_cold(M[s]);
+    }
   }
   Eend = E[4];
 }
@@ -1623,7 +1683,7 @@ MP_HD void integrator_load(const WalkerRec& r, double C, double t_start, Integra
   in.omega = r.y0;
   in.h = r.h0;
   in.k1 = r.k1;
-  in.facold = 1.0e-4f;
+  in.lfacold = StepControl::l_facold_min;
   in.rejected = 0;
   in.n_rhs = r.n_rhs;
   in.n_steps = 0;
