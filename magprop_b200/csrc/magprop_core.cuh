@@ -863,7 +863,8 @@ MP_HD double spin_g(const Spec& sp, const Walker& w, const StageDisc& d, double 
   }
   // tanh(n (w - 1)); beyond |2x| = 38.2 it is +-1 to the last bit.  Inside, 1e-13 absolute is ample for the
   // integrator (the luminosity stage has its own, full-precision evaluation): degree-10 exp, second-order
-  // reciprocal.
+  // reciprocal.  (Folding the constant factors of 2x into one fused multiply-add on omega, and the cap test into
+  // a comparison with 1/omega -- two multiplications fewer on the serial chain -- measured 0.6 % SLOWER.)
   const double x2 = fma(sp.rhs_n2, fast, -sp.rhs_n2);
   double th;
   if (fabs(x2) > 38.2) th = copysign(1.0, x2);
@@ -954,6 +955,18 @@ MP_HD double dense_eval(const Integrator& in, double tq) {
   return fma(th, fma(th1, fma(th, fma(th1, in.r5, in.r4), in.r3), in.r2), in.r1);
 }
 // The same with 1/hs supplied: a run of nodes inside one step shares the division.
+// 1/hs for the dense output's local coordinate (hs > 0, normal): Newton on the MUFU seed, no IEEE-division fix-up.
+MP_HD double rcp_step(double x) {
+#if defined(__CUDA_ARCH__)
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));       // ~2^-22
+  double e = fma(-x, r, 1.0);
+  e = fma(e, e, e);
+  return fma(r, e, r);                                         // e^3: ~2^-64
+#else
+  return 1.0 / x;
+#endif
+}
 MP_HD double dense_eval_r(const Integrator& in, double tq, double ihs) {
   const double th = (tq - in.t0) * ihs;
   const double th1 = 1.0 - th;
@@ -1182,7 +1195,7 @@ MP_HD int step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, const
 #endif
   const double esum = fma(DP::e7(), k7, fma(DP::e6(), k6, fma(DP::e5(), k5, fma(DP::e4(), k4, fma(DP::e3(), k3, DP::e1() * k1)))));
   const double errv = h * esum;
-  const double sk = sp.rtol_y * fmax(fabs(y), fabs(ynew));
+  const double sk = sp.rtol_y * ((ynew > y) ? ynew : y);   // (y = omega^-2 > 0; a NaN or negative ynew comes with a NaN error)
   const double aerr = fabs(errv);
   const bool accept = aerr <= sk;                 // false for NaN
   const float lerr = log2_error_ratio(aerr, sk);
@@ -1714,7 +1727,7 @@ MP_HD int drain_nodes(const Integrator& in, int jn, int Nn, const double* node_t
   if (jn >= Nn) return jn;
   double tn = ldd(node_t + jn);
   if (!(tn <= in.t)) return jn;
-  const double ihs = 1.0 / in.hs;
+  const double ihs = rcp_step(in.hs);
   do {
     const double v = dense_eval_r(in, tn, ihs);
     row[jn * rstride] = STIFF ? 1.0 / (v * v) : v;

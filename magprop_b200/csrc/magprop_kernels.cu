@@ -476,7 +476,10 @@ advance_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k
 #define MP_REFILL_PATIENCE 32
 #endif
     waited = idle ? waited + 1 : 0;
-    if (idle && !empty && (idle == kFull || waited > MP_REFILL_PATIENCE)) {
+    // (one warp-wide vote per trip: whether any lane holds a walker follows from `idle` unless lanes were just refilled)
+    if (!(idle && !empty && (idle == kFull || waited > MP_REFILL_PATIENCE))) {
+      if (idle == kFull) break;
+    } else {
       waited = 0;
       const int leader = __ffs(idle) - 1;
       int base = 0;
@@ -511,8 +514,8 @@ advance_kernel(const __grid_constant__ Problem p, const __grid_constant__ Work k
         row = k.ybuf + (size_t)wid * k.ws;
         jn = drain_nodes<STIFF>(in, jn, Nn, node_t, row, k.ns);      // a node at the starting time
       }
+      if (!__any_sync(kFull, have)) break;
     }
-    if (!__any_sync(kFull, have)) break;
     // ---- one step for every lane that holds a walker (a fresh walker whose nodes are all delivered
     // already, or whose initialisation failed, skips it)
     if (have && jn < Nn && in.status == kWalkerOk) {
