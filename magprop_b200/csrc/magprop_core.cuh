@@ -1761,10 +1761,15 @@ MP_HD double reduce_rows(const Spec& sp, const DataView& dv, const Walker& w, co
   const int Nn = dv.n_nodes;
   double chi2 = 0.0, Lprev = 0.0;
   int idat = 0;
+  // (the node values come from HBM, one per walker and node: the next node's is requested before this node's
+  // luminosity is worked out, so its latency hides behind that arithmetic)
+  double y_next = Nn > 0 ? row[0] : 0.0;
   for (int j = 0; j < Nn; ++j) {
     const double tn = ldd(dv.node_t + j);
+    const double y_node = y_next;
+    if (j + 1 < Nn) y_next = row[(size_t)(j + 1) * rstride];
     double M, om;
-    const Lum L = node_luminosity(sp, w, tn, dv.t_start, row[j * rstride], MODE == kModeCurves && state_out, M, om);
+    const Lum L = node_luminosity(sp, w, tn, dv.t_start, y_node, MODE == kModeCurves && state_out, M, om);
     if (MODE == kModeCurves) {
       out[(0 * Nn + j) * ostride] = L.tot * 1.0e-50;            // (/1e50, funcs.py:231,236, as one multiplication: <= 1 ulp)
       out[(1 * Nn + j) * ostride] = L.prop * 1.0e-50;
