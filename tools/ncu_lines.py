@@ -25,13 +25,26 @@ print(f"total warp instructions {tot_w:,}  active threads per instruction {tot_t
 for wi, ti, f, ln, src in sorted(lines, reverse=True)[:top]:
     print(f"{100 * wi / tot_w:5.1f}%  {wi:>12,}  thr {ti / wi:5.1f}  {f}:{ln}  {src[:110]}")
 
-# ---- by region of magprop_core.cuh (line ranges of the functions on the integrator's path)
-REGIONS = [("bits/table_locate/poly/ld2", 108, 233), ("exp_c", 313, 339), ("pow_m17_fast/cold", 341, 387), ("pow_m17_seeded(1)", 388, 438),
-           ("rsqrt_pos(2)/rcp_pos", 656, 696), ("exp_small", 697, 720), ("exp_small10+rcp_pos2", 721, 751), ("spin_g", 790, 850),
-           ("dense_eval", 875, 886), ("controller", 970, 986), ("breakup_sliding", 1014, 1048), ("locate_kink", 1049, 1091),
-           ("step_spin_chain", 1092, 1196), ("disc_stages<N>", 1197, 1238), ("disc_stages_dp5", 1239, 1277),
-           ("integrator_step", 1278, 1316), ("spin_fJ", 1326, 1376), ("radau_step", 1377, 1506), ("load/drain_nodes", 1606, 1655),
-           ("luminosity stage", 596, 655)]
+# ---- by region of magprop_core.cuh: every region runs from the line of its marker to the next marker's
+import os, re
+MARKS = [("bits/table_locate/poly/ld2", r"^MP_HD int64_t dbits"), ("disc tables: series/asymptotics", r"^MP_HD double disc_S_series|^// ---- S\(u\)"),
+         ("exp_c", r"^MP_HD double exp_c"), ("pow_m17_fast/cold", r"^MP_HD double pow_m17_fast"), ("pow_m17_seeded(1)", r"^MP_HD double pow_m17_seeded\("),
+         ("rcp/rsqrt_fast", r"^MP_HD double rcp_fast"), ("walker setup / cold rhs", r"^struct Walker|^MP_HD void walker_setup"),
+         ("luminosity stage", r"^MP_HD Lum luminosity"), ("rsqrt_pos(2)/rcp_pos", r"^MP_HD double rsqrt_pos\("), ("exp_small", r"^MP_HD double exp_small\("),
+         ("exp_small10+rcp_pos2", r"^MP_HD double exp_small10"), ("spin_f", r"^struct StageDisc"), ("spin_g", r"^MP_HD double spin_g\(const Spec& sp, const Walker& w, const StageDisc& d, double y, unsigned& side, unsigned& regime"),
+         ("step control", r"^struct StepControl"), ("Integrator/dense_eval/init", r"^struct Integrator"), ("DP tableau", r"^MP_CONST_QUALIFIER double kDP"),
+         ("breakup_sliding", r"^static bool breakup_sliding_block\("), ("locate_kink", r"^static double locate_kink"), ("step_spin_chain", r"^MP_HD int step_spin_chain"),
+         ("disc_stages<N>", r"^MP_HD void disc_stages\("), ("disc_stages_dp5", r"^MP_HD void disc_stages_dp5"), ("integrator_step", r"^MP_HD bool integrator_step"),
+         ("radau (spin_fJ, radau_step)", r"^struct RadauC"), ("records / load / drain_nodes", r"^struct WalkerRec|^// ---- one walker, in three stages"),
+         ("reduce_rows", r"^MP_HD double reduce_rows")]
+core = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "magprop_b200", "csrc", "magprop_core.cuh")
+src_lines = open(core).read().splitlines()
+starts = []
+for n, pat in MARKS:
+    hit = next((i + 1 for i, l in enumerate(src_lines) if re.search(pat, l) and not l.rstrip().endswith(";")), None)   # (not a declaration)
+    if hit: starts.append((hit, n))
+starts.sort()
+REGIONS = [(n, a, (starts[i + 1][0] - 1 if i + 1 < len(starts) else len(src_lines))) for i, (a, n) in enumerate(starts)]
 agg = collections.OrderedDict((n, [0, 0]) for n, _, _ in REGIONS)
 other = collections.Counter(); other_t = collections.Counter()
 for wi, ti, f, ln, src in lines:
