@@ -1222,11 +1222,13 @@ MP_HD int step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, const
 #ifndef MP_NO_SLIDING
     if (side == 3u && breakup_sliding_block_y(sp, w, d[4], y, ynew, true)) in.status = kWalkerIntegratorFail;
 #endif
-    in.h = in.rejected ? fmin(hnew, h) : hnew;
+    // (plain comparisons: fmin/fmax carry NaN handling the finite step sizes here do not need)
+    double hn = (in.rejected && h < hnew) ? h : hnew;   // no growth right after a rejection
     if (in.h_resume > 0.0) {                      // this was the (short) step that landed on a kink:
-      in.h = fmax(in.h, in.h_resume);             // carry on with the step size in use before it
+      hn = (in.h_resume > hn) ? in.h_resume : hn;  // carry on with the step size in use before it
       in.h_resume = 0.0;
     }
+    in.h = hn;
     in.rejected = 0;
     in.n_steps++;
     // stiffness detection: |lambda| t > 10 (lambda from the last two stages, which share their time)
@@ -1330,7 +1332,8 @@ MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, do
     Eend = w.C * exp_c(w.u0 - u[4]);
     return;
   }
-  const double a = exp_small(fmax(dl * (-1.0 / 90.0), -40.0));
+  const double xa = dl * (-1.0 / 90.0);
+  const double a = exp_small(xa < -40.0 ? -40.0 : xa);
   const double a2 = a * a, a4 = a2 * a2, a8 = a4 * a4, a9 = a8 * a;
   const double a18 = a9 * a9, a27 = a18 * a9, a36 = a18 * a18, a72 = a36 * a36;
   const double E[5] = {Et * a18, Et * a27, Et * a72, Et * (a72 * a8), Et * (a72 * a18)};
