@@ -140,12 +140,10 @@ struct TableAt {
 };
 
 MP_HD int dhi(double x) { return (int)(dbits(x) >> 32); }
-MP_HD double dfromhi(unsigned hi) { return bitsd((int64_t)((uint64_t)hi << 32)); }
 
 // Rows are laid out by (binade, sub-interval), i.e. by the top 11 + MP_DISC_NSUB_LOG2 bits of u, so
 // the row index is one shift and one subtraction of the high word.  The local coordinate is
-// (u - centre) * 2^(NSUB_LOG2 + 1 - e); the centre of the sub-interval and that power of two are
-// both assembled from the high word.  Always yields a loadable row (row 0 when u is outside the
+// (u - centre) * 2^(NSUB_LOG2 + 1 - e) with the centre of the sub-interval, read off the mantissa.  Always yields a loadable row (row 0 when u is outside the
 // table -- u <= 0, subnormal, NaN/inf included) so callers can evaluate unconditionally and patch
 // the rare outside case afterwards.
 MP_HD bool table_locate_safe(double u, TableAt& ta) {
@@ -154,10 +152,12 @@ MP_HD bool table_locate_safe(double u, TableAt& ta) {
   const unsigned idx = (unsigned)((hi >> sh) - ((1023 + MP_DISC_EMIN) << MP_DISC_NSUB_LOG2));
   const bool in = idx < (unsigned)((MP_DISC_EMAX - MP_DISC_EMIN + 1) << MP_DISC_NSUB_LOG2);
   ta.row = &mp_disc_table[in ? idx : 0u][0];
-  const unsigned uh = (unsigned)hi;
-  const double centre = dfromhi((uh & ~((1u << sh) - 1u)) | (1u << (sh - 1)));
-  const double scale = dfromhi(((unsigned)(2046 + MP_DISC_NSUB_LOG2 + 1) << 20) - (uh & 0x7ff00000u));
-  ta.s = (u - centre) * scale;
+  // (the local coordinate from the mantissa bits: see table_locate_fast)
+  const int64_t ub = dbits(u);
+  const unsigned uh = (unsigned)(ub >> 32), ul = (unsigned)ub;
+  const unsigned mh = (((uh << MP_DISC_NSUB_LOG2) | (ul >> (32 - MP_DISC_NSUB_LOG2))) & 0x000fffffu) | 0x3ff00000u;
+  const unsigned ml = ul << MP_DISC_NSUB_LOG2;
+  ta.s = fma(bitsd((int64_t)(((uint64_t)mh << 32) | ml)), 2.0, -3.0);
   return in;
 }
 MP_HD bool table_locate(double u, TableAt& ta) { return table_locate_safe(u, ta); }
@@ -169,10 +169,16 @@ MP_HD bool table_locate_fast(double u, TableAt& ta) {
   const unsigned idx = (unsigned)((hi >> sh) - ((1023 + MP_DISC_EMIN) << MP_DISC_FAST_NSUB_LOG2));
   const bool in = idx < (unsigned)((MP_DISC_EMAX - MP_DISC_EMIN + 1) << MP_DISC_FAST_NSUB_LOG2);
   ta.row = &mp_disc_fast[in ? idx : 0u][0];
-  const unsigned uh = (unsigned)hi;
-  const double centre = dfromhi((uh & ~((1u << sh) - 1u)) | (1u << (sh - 1)));
-  const double scale = dfromhi(((unsigned)(2046 + MP_DISC_FAST_NSUB_LOG2 + 1) << 20) - (uh & 0x7ff00000u));
-  ta.s = (u - centre) * scale;
+  // The local coordinate straight from the mantissa: with u = 2^e (1 + (j + f)/NSUB), f in [0,1) is the mantissa
+  // below its top NSUB_LOG2 bits; shifted up by that many bits under a zero exponent it reads m = 1 + f, and
+  // s = 2f - 1 = 2m - 3 -- exactly the (u - centre) * 2^(NSUB_LOG2 + 1 - e) of the generic form (both are exact),
+  // in four instructions instead of eight.
+  const int64_t ub = dbits(u);
+  const unsigned uh = (unsigned)(ub >> 32), ul = (unsigned)ub;
+  const unsigned mh = (((uh << MP_DISC_FAST_NSUB_LOG2) | (ul >> (32 - MP_DISC_FAST_NSUB_LOG2))) & 0x000fffffu) | 0x3ff00000u;
+  const unsigned ml = ul << MP_DISC_FAST_NSUB_LOG2;
+  const double m = bitsd((int64_t)(((uint64_t)mh << 32) | ml));
+  ta.s = fma(m, 2.0, -3.0);
   return in;
 }
 
