@@ -1224,13 +1224,14 @@ MP_HD int step_spin_chain(const Spec& sp, const Walker& w, Integrator& in, const
     in.k1 = k7;
     // (a step that was aimed at a kink ends on it: from here on the far side's regime holds, whichever
     // side of the kink rounding put the end point on)
-    in.regime = (in.regime & ~3u) | ((in.h_resume > 0.0) ? ((in.regime >> 2) & 3u) : regime_end);
+    const bool landing = in.h_resume > 0.0;
+    in.regime = (in.regime & ~3u) | (landing ? ((in.regime >> 2) & 3u) : regime_end);
 #ifndef MP_NO_SLIDING
     if (side == 3u && breakup_sliding_block_y(sp, w, d[4], y, ynew, true)) in.status = kWalkerIntegratorFail;
 #endif
     // (plain comparisons: fmin/fmax carry NaN handling the finite step sizes here do not need)
     double hn = (in.rejected && h < hnew) ? h : hnew;   // no growth right after a rejection
-    if (in.h_resume > 0.0) {                      // this was the (short) step that landed on a kink:
+    if (landing) {                                // this was the (short) step that landed on a kink:
       hn = (in.h_resume > hn) ? in.h_resume : hn;  // carry on with the step size in use before it
       in.h_resume = 0.0;
     }
@@ -1370,6 +1371,10 @@ MP_HD void disc_stages_dp5(const Spec& sp, const Walker& w, const double* ts, do
 }
 
 MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integrator& in) {
+  // step budget (accepted steps count too): a walker that has used it up and is asked for another step fails.
+  // (Tested on the count alone, before the step -- a step is only asked for while nodes are outstanding; after
+  // the step the test needed t_end, which lives in local memory, and a second comparison: -1.5 %.)
+  if (in.n_steps >= sp.max_steps) { in.status = kWalkerIntegratorFail; return false; }
   const double t = in.t, y = in.omega;
   double h = in.h;
   bool last = false;
@@ -1390,7 +1395,6 @@ MP_HD bool integrator_step(const Spec& sp, const Walker& w, double t_end, Integr
   unsigned regime_trial;
   const int code = step_spin_chain(sp, w, in, t, y, h, tn, d, y_trial, regime_trial);
   if (code == 1) in.E = Eend;
-  if (in.n_steps >= sp.max_steps && in.t < t_end) in.status = kWalkerIntegratorFail;   // step budget (accepted steps count too)
   if (code == 2) {
     // locate the kink and aim the next attempt at it; one within 1e-3 of either end of the trial is
     // left alone (its effect is O(1e-6) of a full crossing): the attempt is repeated as one-sided
