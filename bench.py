@@ -363,9 +363,10 @@ def run_ours(args):
         "how": "achieved = executed FP64 flop of the timed launches (ncu: 2*DFMA+DMUL+DADD thread instructions -- per RHS "
                "evaluation for the integrator, times the RHS evaluations counted live on the device, plus the setup and reduce "
                "stages' per evaluation) / launch time from CUDA events on the launching stream; peak = live DFMA micro-benchmark "
-               "on this GPU (MEASURED_PEAKS.json has no FP64 entry).  The fraction is bounded by the instruction mix: 43 % of the "
+               "on this GPU (MEASURED_PEAKS.json has no FP64 entry).  The fraction is bounded by the instruction mix: %.0f %% of the "
                "integrator's FP64 arithmetic instructions are plain multiplies (1 flop per pipe slot instead of 2), so a fully "
-               "busy pipe would read 0.76; fp64_pipe_active_pct_ncu is the pipe's occupancy itself",
+               "busy pipe would read %.2f; fp64_pipe_active_pct_ncu is the pipe's occupancy itself"
+               % (100.0 * NCU["dmul_per_rhs"] / NCU["fp64_inst_per_rhs"], NCU["flop_per_rhs"] / (2.0 * NCU["fp64_inst_per_rhs"])),
         "flop_per_rhs_executed": NCU["flop_per_rhs"], "fp64_inst_per_rhs": NCU["fp64_inst_per_rhs"],
         "setup_plus_reduce_flop_per_eval": stage_flop,
         "fp64_pipe_active_pct_ncu": NCU["fp64_pipe_active_pct"], "ncu_source": NCU["source"],
