@@ -242,3 +242,27 @@ extern "C" int hs_cost_trace(const mp_model_spec* ms, const mp_prior_spec* pr, c
   }
   return 0;
 }
+
+// the tables' local coordinate and row index of u (fast = the explicit integrator's table), for the test of the
+// mantissa-shift form against the centre / scale definition
+extern "C" int hs_table_coord(double u, int fast, double* s, int* row, int* nsub_log2) {
+  TableAt ta;
+  const bool in = fast ? table_locate_fast(u, ta) : table_locate_safe(u, ta);
+  *s = ta.s;
+  *row = fast ? (int)((ta.row - &mp_disc_fast[0][0]) / (long)(sizeof(mp_disc_fast[0]) / sizeof(double)))
+              : (int)((ta.row - &mp_disc_table[0][0]) / (long)(sizeof(mp_disc_table[0]) / sizeof(double)));
+  *nsub_log2 = fast ? MP_DISC_FAST_NSUB_LOG2 : MP_DISC_NSUB_LOG2;
+  return in ? 1 : 0;
+}
+
+// the step-size controller: 1/fac after an accepted (accept != 0) or a rejected step, and the updated log2(facold)
+extern "C" double hs_step_scale(double aerr, double sk, float lfacold, int accept, float* lfacold_new) {
+  const float lerr = log2_error_ratio(aerr, sk);
+  if (accept) {
+    const float g = StepControl::expo1 * lerr - StepControl::beta * lfacold - StepControl::l_safe;
+    *lfacold_new = fmaxf(lerr, StepControl::l_facold_min);
+    return step_scale(-fmaxf(StepControl::l_grow, fminf(StepControl::l_shrink, g)));
+  }
+  *lfacold_new = lfacold;
+  return step_scale(-fminf(StepControl::l_shrink, StepControl::expo1 * lerr - StepControl::l_safe));
+}

@@ -78,6 +78,51 @@ def test_disc_mass_kernel_function(hostsim):
         assert abs(d + hostsim.hs_disc_S(v) - v ** (-5.0 / 3.0)) < 1e-6 * v ** (-5.0 / 3.0) + 1e-7 * abs(d)
 
 
+def test_table_coordinate_from_the_mantissa(hostsim):
+    """Both tables' local coordinate is read off the mantissa bits of u; it must be, bit for bit, the definition the
+    tables were generated with -- (u - centre of the sub-interval) * 2^(NSUB_LOG2 + 1 - e) -- and the row index the
+    sub-interval's number."""
+    rng = np.random.RandomState(3)
+    u = np.concatenate([2.0 ** rng.uniform(-10, 22, 20000), np.ldexp(1.0 + rng.randint(0, 512, 2000) / 512.0, rng.randint(-10, 22, 2000)),
+                        np.nextafter(2.0 ** np.arange(-9, 22), 0.0), 2.0 ** np.arange(-10, 22)])
+    s, row, k = C.c_double(), C.c_int(), C.c_int()
+    hostsim.hs_table_coord.argtypes = [C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    for fast in (0, 1):
+        for v in u:
+            assert hostsim.hs_table_coord(float(v), fast, C.byref(s), C.byref(row), C.byref(k)) == 1
+            m, e = np.frexp(v); m, e = 2.0 * m, e - 1                      # v = m 2^e, 1 <= m < 2
+            nsub = 1 << k.value
+            j = int(np.floor((m - 1.0) * nsub))
+            centre = np.ldexp(1.0 + (j + 0.5) / nsub, int(e))
+            want = np.ldexp(v - centre, k.value + 1 - int(e))
+            assert s.value == want and -1.0 <= s.value < 1.0, (v, s.value, want)
+            assert row.value == (int(e) + 10) * nsub + j
+        for v in (0.0, -1.0, 2.0 ** -11, 2.0 ** 22, np.inf, np.nan):     # outside: a loadable row all the same
+            assert hostsim.hs_table_coord(float(v), fast, C.byref(s), C.byref(row), C.byref(k)) == 0 and row.value == 0
+
+
+def test_step_size_controller_in_the_log_domain(hostsim):
+    """The controller is evaluated in log2 (no divisions): it must be Hairer's dopri5 rule -- accepted:
+    h_new = h / clamp(err^0.17 / facold^0.04 / 0.9, 0.1, 5), facold <- max(err, 1e-4); rejected:
+    h_new = h / min(err^0.17 / 0.9, 5) -- to single precision."""
+    hostsim.hs_step_scale.restype = C.c_double
+    hostsim.hs_step_scale.argtypes = [C.c_double, C.c_double, C.c_float, C.c_int, C.POINTER(C.c_float)]
+    rng = np.random.RandomState(4)
+    lf = C.c_float()
+    for _ in range(2000):
+        sk = 10.0 ** rng.uniform(-18, -4); err = 10.0 ** rng.uniform(-6, 3); facold = max(10.0 ** rng.uniform(-6, 1), 1e-4)
+        got = hostsim.hs_step_scale(err * sk, sk, float(np.log2(facold)), 1, C.byref(lf))
+        want = 1.0 / min(5.0, max(0.1, err ** 0.17 / facold ** 0.04 / 0.9))
+        assert abs(got - want) < 2e-5 * want
+        assert abs(lf.value - np.log2(max(err, 1e-4))) < 1e-4
+        got = hostsim.hs_step_scale(err * sk, sk, float(np.log2(facold)), 0, C.byref(lf))
+        assert abs(got - 1.0 / min(5.0, err ** 0.17 / 0.9)) < 2e-5 * got
+    # a vanishing error grows by the full factor 10, a NaN error shrinks by the full factor 5
+    assert abs(hostsim.hs_step_scale(0.0, 1e-9, -13.0, 1, C.byref(lf)) - 10.0) < 1e-4
+    assert abs(hostsim.hs_step_scale(float("nan"), 1e-9, -13.0, 1, C.byref(lf)) - 0.2) < 1e-6
+    assert abs(hostsim.hs_step_scale(float("nan"), 1e-9, -13.0, 0, C.byref(lf)) - 0.2) < 1e-6
+
+
 def _hs_curves(hostsim, spec, grid, pars, stride=1):
     pars = np.ascontiguousarray(np.atleast_2d(pars), dtype=np.float64)
     W = pars.shape[0]
