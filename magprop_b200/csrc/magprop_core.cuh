@@ -141,6 +141,19 @@ struct TableAt {
 
 MP_HD int dhi(double x) { return (int)(dbits(x) >> 32); }
 
+// 1 + f, where f in [0,1) is the part of u's mantissa below its top K bits (the position of u inside the K-bit
+// sub-interval of its binade): the mantissa shifted up by K bits under a zero exponent.
+template <int K>
+MP_HD double mantissa_below(double u) {
+#if defined(__CUDA_ARCH__)
+  const unsigned uh = (unsigned)__double2hiint(u), ul = (unsigned)__double2loint(u);
+  return __hiloint2double((int)((__funnelshift_l(ul, uh, K) & 0x000fffffu) | 0x3ff00000u), (int)(ul << K));
+#else
+  const uint64_t ub = (uint64_t)dbits(u);
+  return bitsd((int64_t)(((ub << K) & 0x000fffffffffffffULL) | 0x3ff0000000000000ULL));
+#endif
+}
+
 // Rows are laid out by (binade, sub-interval), i.e. by the top 11 + MP_DISC_NSUB_LOG2 bits of u, so
 // the row index is one shift and one subtraction of the high word.  The local coordinate is
 // (u - centre) * 2^(NSUB_LOG2 + 1 - e) with the centre of the sub-interval, read off the mantissa.  Always yields a loadable row (row 0 when u is outside the
@@ -153,11 +166,7 @@ MP_HD bool table_locate_safe(double u, TableAt& ta) {
   const bool in = idx < (unsigned)((MP_DISC_EMAX - MP_DISC_EMIN + 1) << MP_DISC_NSUB_LOG2);
   ta.row = &mp_disc_table[in ? idx : 0u][0];
   // (the local coordinate from the mantissa bits: see table_locate_fast)
-  const int64_t ub = dbits(u);
-  const unsigned uh = (unsigned)(ub >> 32), ul = (unsigned)ub;
-  const unsigned mh = (((uh << MP_DISC_NSUB_LOG2) | (ul >> (32 - MP_DISC_NSUB_LOG2))) & 0x000fffffu) | 0x3ff00000u;
-  const unsigned ml = ul << MP_DISC_NSUB_LOG2;
-  ta.s = fma(bitsd((int64_t)(((uint64_t)mh << 32) | ml)), 2.0, -3.0);
+  ta.s = fma(mantissa_below<MP_DISC_NSUB_LOG2>(u), 2.0, -3.0);
   return in;
 }
 MP_HD bool table_locate(double u, TableAt& ta) { return table_locate_safe(u, ta); }
@@ -173,12 +182,7 @@ MP_HD bool table_locate_fast(double u, TableAt& ta) {
   // below its top NSUB_LOG2 bits; shifted up by that many bits under a zero exponent it reads m = 1 + f, and
   // s = 2f - 1 = 2m - 3 -- exactly the (u - centre) * 2^(NSUB_LOG2 + 1 - e) of the generic form (both are exact),
   // in four instructions instead of eight.
-  const int64_t ub = dbits(u);
-  const unsigned uh = (unsigned)(ub >> 32), ul = (unsigned)ub;
-  const unsigned mh = (((uh << MP_DISC_FAST_NSUB_LOG2) | (ul >> (32 - MP_DISC_FAST_NSUB_LOG2))) & 0x000fffffu) | 0x3ff00000u;
-  const unsigned ml = ul << MP_DISC_FAST_NSUB_LOG2;
-  const double m = bitsd((int64_t)(((uint64_t)mh << 32) | ml));
-  ta.s = fma(m, 2.0, -3.0);
+  ta.s = fma(mantissa_below<MP_DISC_FAST_NSUB_LOG2>(u), 2.0, -3.0);
   return in;
 }
 
@@ -411,7 +415,8 @@ MP_HD double pow_m17_seeded(double x) {
   const long long xb = __double_as_longlong(x);
   const unsigned hi = (unsigned)(xb >> 32), lo = (unsigned)xb;
   if (!(hi - (897u << 20) < (253u << 20))) return pow_m17_cold(x);   // outside float range, x <= 0, NaN
-  const float xf = __uint_as_float(((hi - (896u << 20)) << 3) | (lo >> 29));
+  // ((hi - (896 << 20)) << 3) | (lo >> 29): one funnel shift and one add (896 << 23 = -0x40000000 mod 2^32)
+  const float xf = __uint_as_float(__funnelshift_l(lo, hi, 3) + 0x40000000u);
   float lg, sf;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(lg * (-1.0f / 7.0f)));
@@ -435,7 +440,8 @@ MP_HD double pow_m17_seeded1(double x) {
   const long long xb = __double_as_longlong(x);
   const unsigned hi = (unsigned)(xb >> 32), lo = (unsigned)xb;
   if (!(hi - (897u << 20) < (253u << 20))) return pow_m17_cold(x);   // outside float range, x <= 0, NaN
-  const float xf = __uint_as_float(((hi - (896u << 20)) << 3) | (lo >> 29));
+  // ((hi - (896 << 20)) << 3) | (lo >> 29): one funnel shift and one add (896 << 23 = -0x40000000 mod 2^32)
+  const float xf = __uint_as_float(__funnelshift_l(lo, hi, 3) + 0x40000000u);
   float lg, sf;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(lg * (-1.0f / 7.0f)));
@@ -463,7 +469,8 @@ MP_HD double pow_m17_seeded1_inrange(double x) {
 #if defined(__CUDA_ARCH__) && !defined(MP_POW_CVT)
   const long long xb = __double_as_longlong(x);
   const unsigned hi = (unsigned)(xb >> 32), lo = (unsigned)xb;
-  const float xf = __uint_as_float(((hi - (896u << 20)) << 3) | (lo >> 29));
+  // ((hi - (896 << 20)) << 3) | (lo >> 29): one funnel shift and one add (896 << 23 = -0x40000000 mod 2^32)
+  const float xf = __uint_as_float(__funnelshift_l(lo, hi, 3) + 0x40000000u);
   float lg, sf;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(xf));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(lg * (-1.0f / 7.0f)));
